@@ -1,0 +1,212 @@
+/*
+ * ngp_b200.h — C-ABI of the B200-native Instant-NGP hot path.
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one Taichi
+ * kernel (or one torch op sequence) of taichi-dev/taichi-nerfs; the reference
+ * interface each one stands in for is cited as `file:line` (relative to the
+ * reference checkout).  The reference's "FFI" is Taichi's ndarray binding:
+ * caller-allocated, contiguous torch tensors passed by raw device pointer on
+ * the caller's CUDA stream; kernels return nothing and write into caller
+ * buffers.  We keep exactly that contract:
+ *
+ *   - all buffers are caller-owned device memory (plain pointers + sizes);
+ *   - every call is asynchronous on the `stream` argument (a cudaStream_t
+ *     passed as void*); no call synchronises the device;
+ *   - return value: 0 = ok, <0 = argument error, >0 = cudaError_t;
+ *     `ngp_last_error()` holds a human readable message for the calling thread;
+ *   - no torch / ATen types appear in any signature.
+ *
+ * The CPU oracle (oracle/ngp_oracle.c, TEST INFRASTRUCTURE ONLY) exports the
+ * same signatures with a `_cpu` suffix and without the stream argument.
+ */
+#ifndef NGP_B200_H
+#define NGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGP_MAX_LEVELS 16
+
+/* dtype tags for `void*` tensor arguments */
+#define NGP_F32 0
+#define NGP_F16 1
+
+/*
+ * Multiresolution hash-grid layout.  Mirrors what HashEncoder.__init__ derives
+ * (modules/hash_encoder.py:183-208 / modules/hash_encoder_half.py:256-284) plus
+ * the per-level `scale`/`resolution` that the Taichi kernel recomputes per
+ * thread in f32 (modules/hash_encoder.py:73-80,103-104).  They are computed
+ * once on the host (f32 semantics) and handed to both the oracle and the CUDA
+ * kernels so the two can never disagree on a knife-edge `expf`.
+ */
+typedef struct ngp_hash_layout {
+    int32_t  n_levels;               /* L (<= NGP_MAX_LEVELS)                    */
+    int32_t  feat_dim;               /* F: features per level (2 or 4)           */
+    int32_t  begin_fast_hash_level;  /* first level indexed by the xor-prime hash */
+    int32_t  reserved;
+    int32_t  offsets[NGP_MAX_LEVELS];     /* first entry of each level (entries)   */
+    int32_t  map_sizes[NGP_MAX_LEVELS];   /* entries per level                     */
+    float    scales[NGP_MAX_LEVELS];      /* base_res*exp(l*log_b) - 1     (f32)   */
+    uint32_t resolutions[NGP_MAX_LEVELS]; /* ceil(scale)+1                         */
+} ngp_hash_layout;
+
+/* Weights of the tiny NGP MLP (modules/networks.py:111-132): no biases.
+ * Row-major [out, in] exactly like torch.nn.Linear.weight, fp32 master copy. */
+typedef struct ngp_mlp_weights {
+    const float* w1;   /* xyz_encoder.hidden_layers.0.weight  [64,32] */
+    const float* w2;   /* xyz_encoder.output_layer.weight     [16,64] */
+    const float* w3;   /* rgb_net.hidden_layers.0.weight      [64,32] */
+    const float* w4;   /* rgb_net.hidden_layers.1.weight      [64,64] */
+    const float* w5;   /* rgb_net.output_layer.weight         [ 3,64] */
+} ngp_mlp_weights;
+
+#define NGP_MLP_W1 (64 * 32)
+#define NGP_MLP_W2 (16 * 64)
+#define NGP_MLP_W3 (64 * 32)
+#define NGP_MLP_W4 (64 * 64)
+#define NGP_MLP_W5 (3 * 64)
+#define NGP_MLP_PARAMS (NGP_MLP_W1 + NGP_MLP_W2 + NGP_MLP_W3 + NGP_MLP_W4 + NGP_MLP_W5) /* 9408 */
+
+/* ---- library ------------------------------------------------------------- */
+int         ngp_version(void);
+const char* ngp_last_error(void);
+/* number of kernel launches this library has issued in the calling process */
+int64_t     ngp_launch_count(void);
+
+/* ---- a1: ray / AABB slab test ------------------------------------------- */
+/* replaces ray_aabb_intersect, modules/intersection.py:8-37 (wrapper :40-55) */
+int ngp_ray_aabb_intersect(const float* rays_o, const float* rays_d, float scale,
+                           float* hits_t, int64_t n_rays, void* stream);
+
+/* ---- a2: occupancy-grid ray marching, training -------------------------- */
+/* replaces raymarching_train_kernel, modules/ray_march.py:8-123.
+ * Split in two launches so the host wrapper (or a fused step) can size the
+ * sample buffers from `counter[0]` instead of allocating n_rays*max_samples
+ * rows (modules/ray_march.py:149-168):
+ *   _count : pass 1 (ray_march.py:45-74) -> rays_a[r] = (r, exclusive-scan, n),
+ *            counter[0] = total samples, counter[1] = n_rays.
+ *            Layout is deterministic (ray order), unlike the atomics of :76-81.
+ *   _write : pass 2 (ray_march.py:86-123) -> xyzs, dirs, deltas, ts.
+ *            Rays whose segment would exceed `capacity` rows write nothing and
+ *            get rays_a[r,2] = 0; counter[0] is clamped accordingly. */
+int ngp_raymarching_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
+                                const uint8_t* density_bitfield, const float* noise,
+                                int cascades, int grid_size, float scale, float exp_step_factor,
+                                int max_samples, int32_t* counter, int32_t* rays_a,
+                                int64_t n_rays, void* stream);
+int ngp_raymarching_train_write(const float* rays_o, const float* rays_d, const float* hits_t,
+                                const uint8_t* density_bitfield, const float* noise,
+                                int cascades, int grid_size, float scale, float exp_step_factor,
+                                int32_t* counter, int32_t* rays_a,
+                                float* xyzs, float* dirs, float* deltas, float* ts,
+                                int64_t n_rays, int64_t capacity, void* stream);
+
+/* ---- a3: occupancy-grid ray marching, test time -------------------------- */
+/* replaces raymarching_test_kernel, modules/ray_march.py:197-268.
+ * hits_t[r,0] is advanced in place (ray_march.py:257). */
+int ngp_raymarching_test(const float* rays_o, const float* rays_d, float* hits_t,
+                         const int64_t* alive_indices, const uint8_t* density_bitfield,
+                         int cascades, int grid_size, float scale, float exp_step_factor,
+                         int max_samples, int64_t* ray_indices, uint8_t* valid_mask,
+                         float* deltas, float* ts, int32_t* samples_counter,
+                         int64_t n_alive, void* stream);
+
+/* ---- a4/a5: multiresolution hash-grid encoding --------------------------- */
+/* forward: replaces hash_encoder_kernel, modules/hash_encoder.py:89-143 (fp32
+ * table, fp32 out [n, L*F]) and modules/hash_encoder_half.py:112-161 (fp16 table,
+ * fp16 accumulate, fp16 out [n, L, F]).  `dtype` selects NGP_F32 / NGP_F16 for
+ * both `table` and `out`. */
+int ngp_hash_encode_fwd(const float* xyz, const void* table, const ngp_hash_layout* layout,
+                        void* out, int dtype, int64_t n, void* stream);
+/* backward wrt the table: replaces hash_encoder_kernel.grad (Taichi autodiff,
+ * modules/hash_encoder.py:265-277) and hash_encoder_backward_kernel
+ * (modules/hash_encoder_half.py:164-213).  grad_table is fp32 [entries*F] and is
+ * ACCUMULATED into (caller zeroes it, hash_encoder_half.py:350-352). */
+int ngp_hash_encode_bwd(const float* xyz, const void* dout, int dout_dtype,
+                        const ngp_hash_layout* layout, float* grad_table,
+                        int64_t n, void* stream);
+/* backward wrt the input position (the reference returns None here,
+ * hash_encoder.py:277; semantics from notebooks/autodiff.ipynb cell 2):
+ * dx[n,3] = d out / d xyz contracted with dout. */
+int ngp_hash_encode_bwd_input(const float* xyz, const void* table, const void* dout, int dtype,
+                              const ngp_hash_layout* layout, float* dx,
+                              int64_t n, void* stream);
+
+/* ---- a6: spherical-harmonics direction encoding -------------------------- */
+/* replaces dir_encoder, modules/spherical_harmonics.py:7-42 */
+int ngp_dir_encode(const float* dirs, float* out, int64_t n, void* stream);
+
+/* ---- a7: fused NGP MLP (sigma net + SH + rgb net) ------------------------- */
+/* replaces NGP.forward's network part, modules/networks.py:136-166 with
+ * MLP.forward :369-380 under torch.autocast(fp16) (train.py:177):
+ *   emb [n,32] (fp16 or fp32), dirs [n,3] fp32 (un-normalised)
+ *   -> sigmas [n] fp32, rgbs [n,3] fp16, h [n,16] fp16 (geometry feature)
+ * With `save` != NULL the activations needed by the backward are stored there
+ * (ngp_mlp_save_bytes(n) bytes). */
+int64_t ngp_mlp_save_bytes(int64_t n);
+int ngp_mlp_fwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w,
+                float* sigmas, void* rgbs_f16, void* save, int64_t n, void* stream);
+/* backward: dsigmas [n] fp32, drgbs [n,3] fp16 -> demb [n,32] (emb dtype) and
+ * fp32 weight gradients ACCUMULATED into grad_w (NGP_MLP_PARAMS floats, order
+ * w1|w2|w3|w4|w5). */
+int ngp_mlp_bwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w,
+                const void* save, const float* dsigmas, const void* drgbs_f16,
+                void* demb, float* grad_w, int64_t n, void* stream);
+
+/* ---- a8: volume-rendering compositing, training --------------------------- */
+/* replaces volume_rendering_kernel, modules/volume_train.py:6-48.
+ * rgbs may be fp16 (autocast) or fp32.  Outputs are indexed by ray id
+ * (rays_a[n,0]).  ws is written for every sample (0 after early termination —
+ * the reference leaves those uninitialised, volume_train.py:91-94). */
+int ngp_composite_train_fwd(const float* sigmas, const void* rgbs, int rgbs_dtype,
+                            const float* deltas, const float* ts, const int32_t* rays_a,
+                            float T_threshold, int32_t* total_samples, float* opacity,
+                            float* depth, float* rgb, float* ws,
+                            int64_t n_rays, int64_t n_samples, void* stream);
+/* replaces volume_rendering_kernel.grad (Taichi autodiff), volume_train.py:131-175 */
+int ngp_composite_train_bwd(const float* dL_dopacity, const float* dL_ddepth,
+                            const float* dL_drgb, const float* dL_dws,
+                            const float* sigmas, const void* rgbs, int rgbs_dtype,
+                            const float* deltas, const float* ts, const int32_t* rays_a,
+                            const float* opacity, const float* depth, const float* rgb,
+                            float T_threshold, float* dL_dsigmas, void* dL_drgbs,
+                            int64_t n_rays, int64_t n_samples, void* stream);
+
+/* ---- a9: incremental compositing, test time ------------------------------- */
+/* replaces composite_test, modules/volume_render_test.py:4-54 (in place) */
+int ngp_composite_test(const float* sigmas, const void* rgbs, int rgbs_dtype,
+                       const float* deltas, const float* ts, const int64_t* pack_info,
+                       int64_t* alive_indices, float T_threshold,
+                       float* opacity, float* depth, float* rgb,
+                       int64_t n_alive, void* stream);
+
+/* ---- occupancy-grid helpers ---------------------------- */
+/* replaces packbits, modules/utils.py:157-169 */
+int ngp_packbits(const float* density_grid, float density_threshold,
+                 uint8_t* density_bitfield, int64_t n_bytes, void* stream);
+/* replaces morton3D_kernel / morton3D_invert_kernel, modules/utils.py:120-154 */
+int ngp_morton3d(const int32_t* coords, int32_t* indices, int64_t n, void* stream);
+int ngp_morton3d_invert(const int32_t* indices, int32_t* coords, int64_t n, void* stream);
+
+/* ---- a12: fused optimizer pass ---------------------------------------------- */
+/* replaces GradScaler.unscale_ + inf check + torch.optim.Adam(eps=1e-15) step
+ * (train.py:137-156,197-201) in ONE pass over the parameters:
+ *   g = grad * inv_scale;  skip everything if *found_inf != 0;
+ *   m,v update; p -= lr * mhat / (sqrt(vhat) + eps);
+ *   optionally refresh the fp16 shadow copy (hash_encoder_half.py:367) and
+ *   zero the gradient (optimizer.zero_grad, train.py:197).
+ * `step` is the 1-based Adam step count used for bias correction. */
+int ngp_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                  void* param_f16_or_null, const int32_t* found_inf_or_null,
+                  float lr, float beta1, float beta2, float eps, float inv_scale,
+                  int32_t step, int zero_grad, int64_t n, void* stream);
+/* sets *found_inf = 1 if any element of grad is non-finite (GradScaler check) */
+int ngp_check_finite(const float* grad, int64_t n, int32_t* found_inf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGP_B200_H */

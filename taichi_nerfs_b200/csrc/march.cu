@@ -1,0 +1,385 @@
+// march.cu — ray/AABB intersection and occupancy-grid ray marching (train + test).
+//
+// Semantics follow modules/intersection.py:8-37, modules/ray_march.py:8-123,197-268 and the
+// device helpers modules/utils.py:54-117 of the reference, in strict fp32 source order (every
+// op an explicit *_rn intrinsic) so that sample positions are bit-identical to the CPU oracle.
+//
+// B200 notes: these kernels are latency-bound integer/fp32 work over a 256 KiB..1.5 MiB
+// bitfield that lives in L1/L2 — there is nothing for tensor cores here.  Training march is
+// count -> single-CTA scan -> write, giving a deterministic, ray-ordered sample layout without
+// the global atomics (ray_march.py:76-81) or the n_rays*1024-row scratch (ray_march.py:149-168).
+#include "common.cuh"
+
+namespace {
+
+constexpr float kNear = 0.01f;                                      // utils.py:13
+constexpr float kSqrt3MaxSamples = (float)(1.7320508075688772 / 1024);  // utils.py:15
+constexpr float kSqrt3x2 = (float)(1.7320508075688772 * 2);             // utils.py:16
+
+__device__ __forceinline__ float calc_dt(float t, float esf, float dt_max) {  // utils.py:54-57
+    return fminf(fmaxf(f_mul(t, esf), kSqrt3MaxSamples), dt_max);
+}
+
+__device__ __forceinline__ int frexp_bit(float x) {  // utils.py:60-75
+    int exponent = 0;
+    if (x != 0.0f) {
+        uint32_t bits = __float_as_uint(x);
+        exponent = (int)((bits & 0x7f800000u) >> 23) - 127;
+        bits = (bits & 0x7fffffu) | 0x3f800000u;
+        const float frac = __uint_as_float(bits);
+        if (frac < 0.5f) exponent -= 1;
+        else if (frac > 1.0f) exponent += 1;
+    }
+    return exponent;
+}
+
+__device__ __forceinline__ uint32_t expand_bits(uint32_t v) {  // utils.py:95-100
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t morton3d(uint32_t x, uint32_t y, uint32_t z) {
+    return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2);
+}
+__device__ __forceinline__ float fsign(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+
+struct Ray {
+    float o[3], d[3], dinv[3];
+};
+
+struct MarchParams {
+    const uint8_t* __restrict__ bits;
+    int cascades;
+    int grid_size;
+    float gsf;       // (float)grid_size
+    float gs_inv;    // 1/gsf
+    uint32_t gs3;    // grid_size^3
+    float scale;
+    float esf;
+    float dt_max;    // SQRT3_2*scale/grid_size
+};
+
+__device__ __forceinline__ void load_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                         int64_t r, Ray& ray) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        ray.o[k] = rays_o[r * 3 + k];
+        ray.d[k] = rays_d[r * 3 + k];
+        ray.dinv[k] = f_div(1.0f, ray.d[k]);
+    }
+}
+
+// One loop iteration of ray_march.py:45-74.  Occupied: returns true with xyz/dt set.
+// Empty: advances t past the cell exit (ray_march.py:66-74) and returns false.
+__device__ __forceinline__ bool march_step(const MarchParams& p, const Ray& ray, float& t, float xyz[3], float& dt) {
+    const float tt = t;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xyz[k] = f_add(ray.o[k], f_mul(tt, ray.d[k]));
+    dt = calc_dt(tt, p.esf, p.dt_max);
+    int mip = 0;
+    if (p.cascades > 1) {
+        const float mx = fmaxf(fmaxf(fabsf(xyz[0]), fabsf(xyz[1])), fabsf(xyz[2]));
+        const int m_pos = min(p.cascades - 1, max(0, frexp_bit(mx) + 1));            // utils.py:78-84
+        const int m_dt = min(p.cascades - 1, max(0, frexp_bit(f_mul(dt, p.gsf))));   // utils.py:87-92
+        mip = max(m_pos, m_dt);
+    }
+    // pow(2, mip-1), exact
+    const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + mip - 1) << 23), p.scale);
+    const float mip_bound_inv = f_div(1.0f, mip_bound);
+    float nxyz[3];
+    uint32_t u[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = f_mul(f_mul(0.5f, f_add(f_mul(xyz[k], mip_bound_inv), 1.0f)), p.gsf);
+        v = fminf(fmaxf(v, 0.0f), f_sub(p.gsf, 1.0f));
+        nxyz[k] = v;
+        u[k] = __float2uint_rz(v);
+    }
+    const uint32_t idx = (uint32_t)mip * p.gs3 + morton3d(u[0], u[1], u[2]);
+    const uint32_t occ = (uint32_t)__ldg(p.bits + (idx >> 3)) & (1u << (idx & 7u));
+    if (occ) return true;
+    float tmin = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float a = f_add(f_add(nxyz[k], 0.5f), f_mul(0.5f, fsign(ray.d[k])));
+        a = f_sub(f_mul(f_mul(a, p.gs_inv), 2.0f), 1.0f);
+        a = f_mul(f_sub(f_mul(a, mip_bound), xyz[k]), ray.dinv[k]);
+        tmin = fminf(tmin, a);
+    }
+    const float t_target = f_add(tt, fmaxf(0.0f, tmin));
+    float tn = f_add(tt, calc_dt(tt, p.esf, p.dt_max));
+    while (tn < t_target) tn = f_add(tn, calc_dt(tn, p.esf, p.dt_max));
+    t = tn;
+    return false;
+}
+
+__device__ __forceinline__ float train_t0(const float* __restrict__ hits_t, const float* __restrict__ noise,
+                                          int64_t r, const MarchParams& p) {
+    float t1 = hits_t[r * 2 + 0];
+    if (t1 >= 0.0f) {  // ray_march.py:36-38
+        const float dt = calc_dt(t1, p.esf, p.dt_max);
+        t1 = f_add(t1, f_mul(dt, noise[r]));
+    }
+    return t1;
+}
+
+// ---- a1 ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ray_aabb_kernel(const float* __restrict__ rays_o,
+                                                       const float* __restrict__ rays_d, float scale,
+                                                       float* __restrict__ hits_t, int64_t n) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const float half = f_div(f_sub(scale, -scale), 2.0f);
+    float t1 = -INFINITY, t2 = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float o = rays_o[r * 3 + k], d = rays_d[r * 3 + k];
+        const float inv = f_div(1.0f, d);
+        const float tmin = f_mul(f_sub(f_sub(0.0f, half), o), inv);
+        const float tmax = f_mul(f_sub(f_add(0.0f, half), o), inv);
+        t1 = fmaxf(t1, fminf(tmin, tmax));
+        t2 = fminf(t2, fmaxf(tmin, tmax));
+    }
+    float2 out;
+    if (t2 > 0.0f) out = make_float2(fmaxf(t1, kNear), t2);
+    else out = make_float2(-1.0f, -1.0f);
+    reinterpret_cast<float2*>(hits_t)[r] = out;
+}
+
+// ---- a2 pass 1 -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) march_count_kernel(const float* __restrict__ rays_o,
+                                                          const float* __restrict__ rays_d,
+                                                          const float* __restrict__ hits_t,
+                                                          const float* __restrict__ noise, MarchParams p,
+                                                          int max_samples, int32_t* __restrict__ rays_a,
+                                                          int64_t n) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    Ray ray;
+    load_ray(rays_o, rays_d, r, ray);
+    const float t2 = hits_t[r * 2 + 1];
+    float t = train_t0(hits_t, noise, r, p);
+    int cnt = 0;
+    float xyz[3], dt;
+    while (0.0f <= t && t < t2 && cnt < max_samples) {  // ray_march.py:43
+        if (march_step(p, ray, t, xyz, dt)) {
+            t = f_add(t, dt);
+            cnt += 1;
+        }
+    }
+    rays_a[r * 3 + 0] = (int32_t)r;
+    rays_a[r * 3 + 2] = cnt;
+}
+
+// exclusive scan of rays_a[:,2] into rays_a[:,1] by one CTA; counter = (total, n_rays)
+__global__ void __launch_bounds__(1024) march_scan_kernel(int32_t* __restrict__ rays_a,
+                                                          int32_t* __restrict__ counter, int64_t n) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t r = base + tid;
+        const int32_t v = r < n ? rays_a[r * 3 + 2] : 0;
+        int32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int32_t w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t nb = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += nb;
+            }
+            warp_tot[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int32_t carry = carry_s;
+        const int32_t warp_off = wid == 0 ? 0 : warp_tot[wid - 1];
+        if (r < n) rays_a[r * 3 + 1] = carry + warp_off + incl - v;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        counter[0] = carry_s;
+        counter[1] = (int32_t)n;
+    }
+}
+
+// ---- a2 pass 2 -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) march_write_kernel(const float* __restrict__ rays_o,
+                                                          const float* __restrict__ rays_d,
+                                                          const float* __restrict__ hits_t,
+                                                          const float* __restrict__ noise, MarchParams p,
+                                                          int32_t* __restrict__ rays_a,
+                                                          int32_t* __restrict__ counter,
+                                                          float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                          float* __restrict__ deltas, float* __restrict__ ts,
+                                                          int64_t n, int64_t capacity) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t start = rays_a[r * 3 + 1];
+    const int cnt = rays_a[r * 3 + 2];
+    if (start + cnt > capacity) {  // does not fit: drop the ray's samples, flag via counter[1] < 0
+        rays_a[r * 3 + 2] = 0;
+        atomicMin(&counter[0], (int32_t)start);  // dropped rays form a suffix: total = first dropped start
+        return;
+    }
+    if (cnt == 0) return;
+    Ray ray;
+    load_ray(rays_o, rays_d, r, ray);
+    const float t2 = hits_t[r * 2 + 1];
+    float t = train_t0(hits_t, noise, r, p);
+    int s = 0;
+    float xyz[3], dt;
+    while (t < t2 && s < cnt) {  // ray_march.py:86
+        if (march_step(p, ray, t, xyz, dt)) {
+            const int64_t i = start + s;
+            xyzs[i * 3 + 0] = xyz[0];
+            xyzs[i * 3 + 1] = xyz[1];
+            xyzs[i * 3 + 2] = xyz[2];
+            dirs[i * 3 + 0] = ray.d[0];
+            dirs[i * 3 + 1] = ray.d[1];
+            dirs[i * 3 + 2] = ray.d[2];
+            ts[i] = t;
+            deltas[i] = dt;
+            t = f_add(t, dt);
+            s += 1;
+        }
+    }
+}
+
+// ---- a3 ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) march_test_kernel(const float* __restrict__ rays_o,
+                                                         const float* __restrict__ rays_d,
+                                                         float* __restrict__ hits_t,
+                                                         const int64_t* __restrict__ alive, MarchParams p,
+                                                         int max_samples, int64_t* __restrict__ ray_indices,
+                                                         uint8_t* __restrict__ valid_mask,
+                                                         float* __restrict__ deltas, float* __restrict__ ts,
+                                                         int32_t* __restrict__ samples_counter, int64_t n_alive) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int64_t r = alive[n];
+    Ray ray;
+    load_ray(rays_o, rays_d, r, ray);
+    float t = hits_t[r * 2 + 0];
+    const float t2 = hits_t[r * 2 + 1];
+    int s = 0;
+    const int64_t base = n * (int64_t)max_samples;
+    float xyz[3], dt;
+    float t_resume = t;  // t right after the last emitted sample (ray_march.py:256-257)
+    while (0.0f < t && t < t2 && s < max_samples) {  // ray_march.py:226 (strict 0 < t)
+        if (march_step(p, ray, t, xyz, dt)) {
+            const int64_t i = base + s;
+            ray_indices[i] = r;
+            valid_mask[i] = 1;
+            ts[i] = t;
+            deltas[i] = dt;
+            t = f_add(t, dt);
+            t_resume = t;
+            s += 1;
+        }
+    }
+    if (s > 0) hits_t[r * 2 + 0] = t_resume;
+    samples_counter[n] = s;
+}
+
+MarchParams make_params(const uint8_t* bits, int cascades, int grid_size, float scale, float esf) {
+    MarchParams p;
+    p.bits = bits;
+    p.cascades = cascades;
+    p.grid_size = grid_size;
+    p.gsf = (float)grid_size;
+    p.gs_inv = 1.0f / p.gsf;
+    p.gs3 = (uint32_t)grid_size * (uint32_t)grid_size * (uint32_t)grid_size;
+    p.scale = scale;
+    p.esf = esf;
+    // SQRT3_2 * scale / grid_size in fp32, mul then div (utils.py:56-57); host IEEE fp32
+    volatile float m = kSqrt3x2 * scale;
+    p.dt_max = m / p.gsf;
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ngp_ray_aabb_intersect(const float* rays_o, const float* rays_d, float scale, float* hits_t,
+                           int64_t n_rays, void* stream) {
+    NGP_REQUIRE(n_rays >= 0, "negative n_rays");
+    if (n_rays == 0) return 0;
+    NGP_REQUIRE(rays_o && rays_d && hits_t, "null pointer");
+    const int block = 256;
+    ray_aabb_kernel<<<(unsigned)((n_rays + block - 1) / block), block, 0, ngp::as_stream(stream)>>>(
+        rays_o, rays_d, scale, hits_t, n_rays);
+    NGP_LAUNCHED("ray_aabb_kernel");
+    return 0;
+}
+
+int ngp_raymarching_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
+                                const uint8_t* density_bitfield, const float* noise, int cascades,
+                                int grid_size, float scale, float exp_step_factor, int max_samples,
+                                int32_t* counter, int32_t* rays_a, int64_t n_rays, void* stream) {
+    NGP_REQUIRE(n_rays >= 0, "negative n_rays");
+    NGP_REQUIRE(counter && (n_rays == 0 || (rays_o && rays_d && hits_t && density_bitfield && noise && rays_a)),
+                "null pointer");
+    NGP_REQUIRE(cascades >= 1 && grid_size >= 1 && grid_size <= 1024, "bad grid");
+    cudaStream_t st = ngp::as_stream(stream);
+    const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
+    if (n_rays > 0) {
+        const int block = 128;
+        march_count_kernel<<<(unsigned)((n_rays + block - 1) / block), block, 0, st>>>(
+            rays_o, rays_d, hits_t, noise, p, max_samples, rays_a, n_rays);
+        NGP_LAUNCHED("march_count_kernel");
+    }
+    march_scan_kernel<<<1, 1024, 0, st>>>(rays_a, counter, n_rays);
+    NGP_LAUNCHED("march_scan_kernel");
+    return 0;
+}
+
+int ngp_raymarching_train_write(const float* rays_o, const float* rays_d, const float* hits_t,
+                                const uint8_t* density_bitfield, const float* noise, int cascades,
+                                int grid_size, float scale, float exp_step_factor, int32_t* counter,
+                                int32_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts,
+                                int64_t n_rays, int64_t capacity, void* stream) {
+    NGP_REQUIRE(n_rays >= 0 && capacity >= 0, "negative size");
+    if (n_rays == 0) return 0;
+    NGP_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && noise && rays_a && counter, "null pointer");
+    NGP_REQUIRE(capacity == 0 || (xyzs && dirs && deltas && ts), "null output");
+    const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
+    const int block = 128;
+    march_write_kernel<<<(unsigned)((n_rays + block - 1) / block), block, 0, ngp::as_stream(stream)>>>(
+        rays_o, rays_d, hits_t, noise, p, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity);
+    NGP_LAUNCHED("march_write_kernel");
+    return 0;
+}
+
+int ngp_raymarching_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_indices,
+                         const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                         float exp_step_factor, int max_samples, int64_t* ray_indices, uint8_t* valid_mask,
+                         float* deltas, float* ts, int32_t* samples_counter, int64_t n_alive, void* stream) {
+    NGP_REQUIRE(n_alive >= 0, "negative n_alive");
+    if (n_alive == 0) return 0;
+    NGP_REQUIRE(rays_o && rays_d && hits_t && alive_indices && density_bitfield && ray_indices && valid_mask &&
+                    deltas && ts && samples_counter,
+                "null pointer");
+    const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
+    const int block = 128;
+    march_test_kernel<<<(unsigned)((n_alive + block - 1) / block), block, 0, ngp::as_stream(stream)>>>(
+        rays_o, rays_d, hits_t, alive_indices, p, max_samples, ray_indices, valid_mask, deltas, ts,
+        samples_counter, n_alive);
+    NGP_LAUNCHED("march_test_kernel");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+// optim.cu — fused optimizer pass: GradScaler unscale + inf-skip + Adam + fp16 shadow refresh +
+// gradient zeroing in ONE read-modify-write sweep over the parameters.
+//
+// Replaces, for the hot path, the separate passes of the reference's step (train.py:197-201):
+// optimizer.zero_grad (4 B/param write), GradScaler.unscale_ (8 B/param), torch.optim.Adam /
+// apex FusedAdam (28 B/param) and the per-forward `hash_table.to(float16)` cast
+// (modules/hash_encoder_half.py:367, 6 B/param).  Here: read p,g,m,v (16 B) + write p,m,v,g=0
+// (16 B) + write fp16 shadow (2 B) = 34 B/param, a pure HBM-streaming kernel (roofline: HBM).
+// Arithmetic follows torch/optim/adam.py::_single_tensor_adam.
+#include "common.cuh"
+
+namespace {
+
+struct AdamArgs {
+    float lr_over_bc1;   // lr / (1 - beta1^t)
+    float bc2_sqrt;      // sqrt(1 - beta2^t)
+    float beta1, beta2, eps, inv_scale;
+    int zero_grad;
+};
+
+__device__ __forceinline__ void adam1(float& p, float& g, float& m, float& v, const AdamArgs& a) {
+    const float gg = g * a.inv_scale;
+    m = m + (gg - m) * (1.0f - a.beta1);                 // exp_avg.lerp_(grad, 1-beta1)
+    v = v * a.beta2 + (1.0f - a.beta2) * gg * gg;        // exp_avg_sq.mul_(beta2).addcmul_(g,g,1-beta2)
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    p = p - a.lr_over_bc1 * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, float* __restrict__ grad,
+                                                   float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
+                                                   __half* __restrict__ shadow, const int32_t* __restrict__ found_inf,
+                                                   AdamArgs a, int64_t n) {
+    const bool skip = found_inf != nullptr && *found_inf != 0;
+    const int64_t n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        if (!skip) {
+            float4 p = reinterpret_cast<float4*>(param)[i];
+            float4 g = reinterpret_cast<const float4*>(grad)[i];
+            float4 m = reinterpret_cast<float4*>(exp_avg)[i];
+            float4 v = reinterpret_cast<float4*>(exp_avg_sq)[i];
+            adam1(p.x, g.x, m.x, v.x, a);
+            adam1(p.y, g.y, m.y, v.y, a);
+            adam1(p.z, g.z, m.z, v.z, a);
+            adam1(p.w, g.w, m.w, v.w, a);
+            reinterpret_cast<float4*>(param)[i] = p;
+            reinterpret_cast<float4*>(exp_avg)[i] = m;
+            reinterpret_cast<float4*>(exp_avg_sq)[i] = v;
+            if (shadow) {
+                __half2 lo = __floats2half2_rn(p.x, p.y), hi = __floats2half2_rn(p.z, p.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                reinterpret_cast<uint2*>(shadow)[i] = pk;
+            }
+        }
+        if (a.zero_grad) reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // tail (n not a multiple of 4)
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (!skip) {
+            float p = param[i], g = grad[i], m = exp_avg[i], v = exp_avg_sq[i];
+            adam1(p, g, m, v, a);
+            param[i] = p;
+            exp_avg[i] = m;
+            exp_avg_sq[i] = v;
+            if (shadow) shadow[i] = __float2half_rn(p);
+        }
+        if (a.zero_grad) grad[i] = 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256) check_finite_kernel(const float* __restrict__ grad, int64_t n,
+                                                           int32_t* __restrict__ found_inf) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 g = reinterpret_cast<const float4*>(grad)[i];
+        // |x| < inf is false for inf and NaN
+        bad |= !(fabsf(g.x) < INFINITY) | !(fabsf(g.y) < INFINITY) | !(fabsf(g.z) < INFINITY) | !(fabsf(g.w) < INFINITY);
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        bad |= !(fabsf(grad[i]) < INFINITY);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(found_inf, 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ngp_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_f16_or_null,
+                  const int32_t* found_inf_or_null, float lr, float beta1, float beta2, float eps, float inv_scale,
+                  int32_t step, int zero_grad, int64_t n, void* stream) {
+    NGP_REQUIRE(n >= 0, "negative n");
+    NGP_REQUIRE(step >= 1, "step is 1-based");
+    if (n == 0) return 0;
+    NGP_REQUIRE(param && grad && exp_avg && exp_avg_sq, "null pointer");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+                         reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq);
+    NGP_REQUIRE((al & 15) == 0, "param/grad/state must be 16-byte aligned");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(param_f16_or_null) & 7) == 0, "fp16 shadow must be 8-byte aligned");
+    AdamArgs a;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    a.lr_over_bc1 = (float)((double)lr / bc1);
+    a.bc2_sqrt = (float)sqrt(bc2);
+    a.beta1 = beta1;
+    a.beta2 = beta2;
+    a.eps = eps;
+    a.inv_scale = inv_scale;
+    a.zero_grad = zero_grad;
+    const int64_t work = (n + 3) / 4;
+    const int64_t max_blocks = (int64_t)ngp::sm_count() * 8;
+    const unsigned grid = (unsigned)min((work + 255) / 256, max_blocks);
+    adam_kernel<<<grid, 256, 0, ngp::as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, (__half*)param_f16_or_null,
+                                                          found_inf_or_null, a, n);
+    NGP_LAUNCHED("adam_kernel");
+    return 0;
+}
+
+int ngp_check_finite(const float* grad, int64_t n, int32_t* found_inf, void* stream) {
+    NGP_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return 0;
+    NGP_REQUIRE(grad && found_inf, "null pointer");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "grad must be 16-byte aligned");
+    const int64_t work = (n + 3) / 4;
+    const int64_t max_blocks = (int64_t)ngp::sm_count() * 8;
+    const unsigned grid = (unsigned)min((work + 255) / 256, max_blocks);
+    check_finite_kernel<<<grid, 256, 0, ngp::as_stream(stream)>>>(grad, n, found_inf);
+    NGP_LAUNCHED("check_finite_kernel");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+// render.cu — SH direction encoding and volume-rendering compositing (train fwd/bwd, test).
+//
+// Semantics: modules/spherical_harmonics.py:16-42, modules/volume_train.py:22-48 (+ its Taichi
+// autodiff transpose, volume_train.py:160-173) and modules/volume_render_test.py:19-54.
+//
+// B200 mapping.  The reference composites with one thread per ray walking up to 1024 samples
+// serially through a global T scratch array.  Here one WARP owns a ray: lanes take consecutive
+// samples (coalesced 128-byte loads), transmittance is a warp prefix product carried across
+// 32-sample chunks, early termination is a ballot, and the per-ray sums are shuffle reductions.
+// Streaming work: HBM/L2-bandwidth bound, ~22 B/sample forward and ~36 B/sample backward.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kChunkCap = 128;  // chunk-start transmittances kept in smem per warp (4096 samples)
+
+// ---- a6: SH degree 4 ---------------------------------------------------------------------------
+__device__ __forceinline__ void sh16(float x, float y, float z, float* e) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    e[0] = 0.28209479177387814f;
+    e[1] = -0.48860251190291987f * y;
+    e[2] = 0.48860251190291987f * z;
+    e[3] = -0.48860251190291987f * x;
+    e[4] = 1.0925484305920792f * xy;
+    e[5] = -1.0925484305920792f * yz;
+    e[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    e[7] = -1.0925484305920792f * xz;
+    e[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    e[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    e[10] = 2.8906114426405538f * xy * z;
+    e[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    e[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    e[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    e[14] = 1.4453057213202769f * z * (x2 - y2);
+    e[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+__global__ void __launch_bounds__(256) dir_encode_kernel(const float* __restrict__ dirs, float* __restrict__ out,
+                                                         int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float e[16];
+    sh16(dirs[i * 3 + 0], dirs[i * 3 + 1], dirs[i * 3 + 2], e);
+    float4* o = reinterpret_cast<float4*>(out + i * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = make_float4(e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
+}
+
+// ---- a8 forward ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_train_fwd_kernel(const float* __restrict__ sigmas, const T* __restrict__ rgbs,
+                           const float* __restrict__ deltas, const float* __restrict__ ts,
+                           const int32_t* __restrict__ rays_a, float thr, int32_t* __restrict__ total_samples,
+                           float* __restrict__ opacity, float* __restrict__ depth, float* __restrict__ rgb,
+                           float* __restrict__ ws, int64_t n_rays) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (n >= n_rays) return;
+    const int64_t ray = rays_a[n * 3 + 0], start = rays_a[n * 3 + 1];
+    const int N = rays_a[n * 3 + 2];
+
+    float r = 0.f, g = 0.f, b = 0.f, dep = 0.f, op = 0.f;
+    float Tc = 1.0f;  // transmittance at the start of the chunk
+    int cnt = 0;
+    bool alive = true;
+    for (int base = 0; base < N; base += 32) {
+        const int k = base + lane;
+        const bool valid = k < N;
+        const int64_t s = start + k;
+        if (!alive) {  // after early termination: only the (defined) zero weights remain
+            if (valid) ws[s] = 0.0f;
+            continue;
+        }
+        float a = 0.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f, tm = 0.f;
+        if (valid) {
+            a = 1.0f - expf(-sigmas[s] * deltas[s]);  // volume_train.py:39
+            c0 = load_as_float(rgbs, s * 3 + 0);
+            c1 = load_as_float(rgbs, s * 3 + 1);
+            c2 = load_as_float(rgbs, s * 3 + 2);
+            tm = ts[s];
+        }
+        const float incl = warp_scan_mul(1.0f - a, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float Tb = Tc * excl;                 // T before this sample
+        const bool active = valid && Tb > thr;      // volume_train.py:38
+        const float w = active ? a * Tb : 0.0f;
+        r += w * c0;
+        g += w * c1;
+        b += w * c2;
+        dep += w * tm;
+        op += w;
+        if (valid) ws[s] = w;
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        const unsigned val = __ballot_sync(0xffffffffu, valid);
+        cnt += __popc(act);
+        if (act != val) alive = false;              // some valid sample fell below the threshold
+        Tc = Tc * __shfl_sync(0xffffffffu, incl, 31);
+    }
+    r = warp_sum(r);
+    g = warp_sum(g);
+    b = warp_sum(b);
+    dep = warp_sum(dep);
+    op = warp_sum(op);
+    if (lane == 0) {
+        rgb[ray * 3 + 0] = r;
+        rgb[ray * 3 + 1] = g;
+        rgb[ray * 3 + 2] = b;
+        depth[ray] = dep;
+        opacity[ray] = op;
+        total_samples[ray] = cnt;
+    }
+}
+
+// ---- a8 backward ---------------------------------------------------------------------------------
+// dL/drgbs[s] = w_s * dL/drgb ;  dL/dsigma[s] = delta_s * (T_{s+1} * G_s - sum_{j>s} w_j G_j)
+// with G_j = dL/drgb . c_j + dL/ddepth * t_j + dL/dopacity + dL/dws_j  (active samples only).
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_train_bwd_kernel(const float* __restrict__ gop, const float* __restrict__ gdep,
+                           const float* __restrict__ grgb, const float* __restrict__ gws,
+                           const float* __restrict__ sigmas, const T* __restrict__ rgbs,
+                           const float* __restrict__ deltas, const float* __restrict__ ts,
+                           const int32_t* __restrict__ rays_a, float thr, float* __restrict__ dsigmas,
+                           T* __restrict__ drgbs, int64_t n_rays) {
+    __shared__ float Tstart_s[kWarpsPerBlock][kChunkCap];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t n = (int64_t)blockIdx.x * kWarpsPerBlock + wid;
+    if (n >= n_rays) return;
+    const int64_t ray = rays_a[n * 3 + 0], start = rays_a[n * 3 + 1];
+    const int N = rays_a[n * 3 + 2];
+    const float gr = grgb[ray * 3 + 0], gg = grgb[ray * 3 + 1], gb = grgb[ray * 3 + 2];
+    const float gd = gdep[ray], go = gop[ray];
+    float* Tstart = Tstart_s[wid];
+
+    // pass 1 (forward): transmittance at every chunk start, index of the last active chunk
+    const int n_chunks = (N + 31) >> 5;
+    int last_chunk = -1;
+    {
+        float Tc = 1.0f;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int k = c * 32 + lane;
+            const bool valid = k < N;
+            const int64_t s = start + k;
+            const float a = valid ? 1.0f - expf(-sigmas[s] * deltas[s]) : 0.0f;
+            const float incl = warp_scan_mul(1.0f - a, lane);
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            const bool active = valid && Tc * excl > thr;
+            const unsigned act = __ballot_sync(0xffffffffu, active);
+            const unsigned val = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0 && c < kChunkCap) Tstart[c] = Tc;
+            if (act) last_chunk = c;
+            if (act != val) {  // terminated inside this chunk: zero the tail's gradients
+                for (int c2 = c; c2 < n_chunks; ++c2) {
+                    const int k2 = c2 * 32 + lane;
+                    if (k2 < N && !(c2 == c && active)) {
+                        const int64_t s2 = start + k2;
+                        dsigmas[s2] = 0.0f;
+                        store_from_float(drgbs, s2 * 3 + 0, 0.0f);
+                        store_from_float(drgbs, s2 * 3 + 1, 0.0f);
+                        store_from_float(drgbs, s2 * 3 + 2, 0.0f);
+                    }
+                }
+                break;
+            }
+            Tc = Tc * __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncwarp();
+
+    // pass 2 (reverse over chunks): exact suffix accumulation
+    float suffix = 0.0f;  // sum_{j in later chunks} w_j G_j
+    for (int c = last_chunk; c >= 0; --c) {
+        float Tc;
+        if (c < kChunkCap) {
+            Tc = Tstart[c];
+        } else {  // rare: > 4096 samples on one ray — recompute the chunk start
+            Tc = Tstart[kChunkCap - 1];
+            for (int c2 = kChunkCap - 1; c2 < c; ++c2) {
+                const int k2 = c2 * 32 + lane;
+                const float a2 = k2 < N ? 1.0f - expf(-sigmas[start + k2] * deltas[start + k2]) : 0.0f;
+                const float in2 = warp_scan_mul(1.0f - a2, lane);
+                Tc = Tc * __shfl_sync(0xffffffffu, in2, 31);
+            }
+        }
+        const int k = c * 32 + lane;
+        const bool valid = k < N;
+        const int64_t s = start + k;
+        float a = 0.f, dl = 0.f, c0 = 0.f, c1 = 0.f, c2v = 0.f, tm = 0.f, gw = 0.f;
+        if (valid) {
+            dl = deltas[s];
+            a = 1.0f - expf(-sigmas[s] * dl);
+            c0 = load_as_float(rgbs, s * 3 + 0);
+            c1 = load_as_float(rgbs, s * 3 + 1);
+            c2v = load_as_float(rgbs, s * 3 + 2);
+            tm = ts[s];
+            gw = gws ? gws[s] : 0.0f;
+        }
+        const float incl = warp_scan_mul(1.0f - a, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float Tb = Tc * excl;
+        const bool active = valid && Tb > thr;
+        const float w = active ? a * Tb : 0.0f;
+        const float G = gr * c0 + gg * c1 + gb * c2v + gd * tm + go + gw;
+        const float wG = w * G;
+        // reverse inclusive scan of wG within the warp
+        float rs = wG;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float nb = __shfl_down_sync(0xffffffffu, rs, o);
+            if (lane + o < 32) rs += nb;
+        }
+        const float later = suffix + (rs - wG);  // sum over j > s
+        if (active) {
+            const float Tnext = Tb * (1.0f - a);
+            dsigmas[s] = dl * (Tnext * G - later);
+            store_from_float(drgbs, s * 3 + 0, w * gr);
+            store_from_float(drgbs, s * 3 + 1, w * gg);
+            store_from_float(drgbs, s * 3 + 2, w * gb);
+        }
+        suffix += __shfl_sync(0xffffffffu, rs, 0);
+    }
+}
+
+// ---- a9 -----------------------------------------------------------------------------------------
+template <typename TRgb>
+__global__ void __launch_bounds__(256)
+composite_test_kernel(const float* __restrict__ sigmas, const TRgb* __restrict__ rgbs, const float* __restrict__ deltas,
+                      const float* __restrict__ ts, const int64_t* __restrict__ pack_info,
+                      int64_t* __restrict__ alive_indices, float thr, float* __restrict__ opacity,
+                      float* __restrict__ depth, float* __restrict__ rgb, int64_t n_alive) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int64_t start = pack_info[n * 2 + 0], steps = pack_info[n * 2 + 1];
+    const int64_t ray = alive_indices[n];
+    if (steps == 0) {  // volume_render_test.py:24-25
+        alive_indices[n] = -1;
+        return;
+    }
+    float T = 1.0f - opacity[ray];
+    float r = 0.f, g = 0.f, b = 0.f, dep = 0.f, op = 0.f;
+    for (int64_t k = 0; k < steps; ++k) {
+        const int64_t s = start + k;
+        const float a = 1.0f - expf(-sigmas[s] * deltas[s]);
+        const float w = a * T;
+        r += w * load_as_float(rgbs, s * 3 + 0);
+        g += w * load_as_float(rgbs, s * 3 + 1);
+        b += w * load_as_float(rgbs, s * 3 + 2);
+        dep += w * ts[s];
+        op += w;
+        T *= 1.0f - a;
+        if (T <= thr) {  // volume_render_test.py:46-48
+            alive_indices[n] = -1;
+            break;
+        }
+    }
+    rgb[ray * 3 + 0] += r;
+    rgb[ray * 3 + 1] += g;
+    rgb[ray * 3 + 2] += b;
+    depth[ray] += dep;
+    opacity[ray] += op;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ngp_dir_encode(const float* dirs, float* out, int64_t n, void* stream) {
+    NGP_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return 0;
+    NGP_REQUIRE(dirs && out, "null pointer");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
+    dir_encode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ngp::as_stream(stream)>>>(dirs, out, n);
+    NGP_LAUNCHED("dir_encode_kernel");
+    return 0;
+}
+
+int ngp_composite_train_fwd(const float* sigmas, const void* rgbs, int rgbs_dtype, const float* deltas,
+                            const float* ts, const int32_t* rays_a, float T_threshold, int32_t* total_samples,
+                            float* opacity, float* depth, float* rgb, float* ws, int64_t n_rays,
+                            int64_t n_samples, void* stream) {
+    NGP_REQUIRE(n_rays >= 0 && n_samples >= 0, "negative size");
+    NGP_REQUIRE(rgbs_dtype == NGP_F32 || rgbs_dtype == NGP_F16, "bad dtype");
+    if (n_rays == 0) return 0;
+    NGP_REQUIRE(rays_a && total_samples && opacity && depth && rgb, "null pointer");
+    NGP_REQUIRE(n_samples == 0 || (sigmas && rgbs && deltas && ts && ws), "null sample pointer");
+    const unsigned grid = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    cudaStream_t st = ngp::as_stream(stream);
+    if (rgbs_dtype == NGP_F16)
+        composite_train_fwd_kernel<__half><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+            sigmas, (const __half*)rgbs, deltas, ts, rays_a, T_threshold, total_samples, opacity, depth, rgb, ws, n_rays);
+    else
+        composite_train_fwd_kernel<float><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+            sigmas, (const float*)rgbs, deltas, ts, rays_a, T_threshold, total_samples, opacity, depth, rgb, ws, n_rays);
+    NGP_LAUNCHED("composite_train_fwd_kernel");
+    return 0;
+}
+
+int ngp_composite_train_bwd(const float* dL_dopacity, const float* dL_ddepth, const float* dL_drgb,
+                            const float* dL_dws, const float* sigmas, const void* rgbs, int rgbs_dtype,
+                            const float* deltas, const float* ts, const int32_t* rays_a, const float* opacity,
+                            const float* depth, const float* rgb, float T_threshold, float* dL_dsigmas,
+                            void* dL_drgbs, int64_t n_rays, int64_t n_samples, void* stream) {
+    (void)opacity; (void)depth; (void)rgb;
+    NGP_REQUIRE(n_rays >= 0 && n_samples >= 0, "negative size");
+    NGP_REQUIRE(rgbs_dtype == NGP_F32 || rgbs_dtype == NGP_F16, "bad dtype");
+    if (n_rays == 0 || n_samples == 0) return 0;
+    NGP_REQUIRE(dL_dopacity && dL_ddepth && dL_drgb && sigmas && rgbs && deltas && ts && rays_a && dL_dsigmas &&
+                    dL_drgbs,
+                "null pointer");
+    const unsigned grid = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    cudaStream_t st = ngp::as_stream(stream);
+    if (rgbs_dtype == NGP_F16)
+        composite_train_bwd_kernel<__half><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+            dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, (const __half*)rgbs, deltas, ts, rays_a, T_threshold,
+            dL_dsigmas, (__half*)dL_drgbs, n_rays);
+    else
+        composite_train_bwd_kernel<float><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+            dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, (const float*)rgbs, deltas, ts, rays_a, T_threshold,
+            dL_dsigmas, (float*)dL_drgbs, n_rays);
+    NGP_LAUNCHED("composite_train_bwd_kernel");
+    return 0;
+}
+
+int ngp_composite_test(const float* sigmas, const void* rgbs, int rgbs_dtype, const float* deltas, const float* ts,
+                       const int64_t* pack_info, int64_t* alive_indices, float T_threshold, float* opacity,
+                       float* depth, float* rgb, int64_t n_alive, void* stream) {
+    NGP_REQUIRE(n_alive >= 0, "negative n_alive");
+    NGP_REQUIRE(rgbs_dtype == NGP_F32 || rgbs_dtype == NGP_F16, "bad dtype");
+    if (n_alive == 0) return 0;
+    NGP_REQUIRE(pack_info && alive_indices && opacity && depth && rgb, "null pointer");
+    const unsigned grid = (unsigned)((n_alive + 255) / 256);
+    cudaStream_t st = ngp::as_stream(stream);
+    if (rgbs_dtype == NGP_F16)
+        composite_test_kernel<__half><<<grid, 256, 0, st>>>(sigmas, (const __half*)rgbs, deltas, ts, pack_info,
+                                                            alive_indices, T_threshold, opacity, depth, rgb, n_alive);
+    else
+        composite_test_kernel<float><<<grid, 256, 0, st>>>(sigmas, (const float*)rgbs, deltas, ts, pack_info,
+                                                           alive_indices, T_threshold, opacity, depth, rgb, n_alive);
+    NGP_LAUNCHED("composite_test_kernel");
+    return 0;
+}
+
+}  // extern "C"
