@@ -1,0 +1,397 @@
+// mlp.cu — the fused NGP MLP (sigma net 32->64->16, SH, rgb net 32->64->64->3) on the
+// 5th-generation tensor cores: tcgen05.mma with operands in shared memory and fp32 accumulators
+// in tensor memory (TMEM), one 128-sample tile per CTA iteration.
+//
+// Replaces, in the reference, five torch.nn.Linear (cuBLAS) calls under torch.autocast(fp16) plus
+// ~10 elementwise/cat/cast kernels: modules/networks.py:136-166 (NGP.density/forward), :369-380
+// (MLP.forward), :18-30 (TruncExp) and modules/spherical_harmonics.py:16-42 (SH is fused into the
+// rgb-net input stage).  Numerics follow autocast: fp16 operands, fp32 accumulate, every layer
+// output rounded to fp16, TruncExp / direction normalisation / SH in fp32.
+//
+// Data layout.  All MMA operands live in shared memory in the canonical UMMA *no-swizzle*
+// ("interleaved") layout: 8x8 fp16 core matrices of 128 contiguous bytes (row stride 16 B);
+// core matrices adjacent along K are LBO = 128 B apart, 8-row groups are SBO = (K/8)*128 B apart.
+// A thread owns one sample row, so an epilogue writes 16-byte chunks that are bank-conflict free
+// per quarter warp, and the same buffer can later be consumed K-major (forward) or MN-major
+// (weight gradients) by swapping LBO/SBO.  Weights (9,408 fp16 = 18.4 KB, W5 zero-padded to 16
+// rows) stay resident in shared memory for the lifetime of the persistent CTA.
+//
+// Roofline: tensor pipe for the MMAs (18,816 FLOP/sample forward) but K is only 32/64, so the
+// kernel is bounded by the TMEM->register->shared epilogue round trips and by 86 B/sample of HBM
+// traffic (emb 64 B + dir 12 B in, sigma 4 B + rgb 6 B out); see DESIGN.md.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTile = 128;          // samples per tile == UMMA M
+constexpr int kThreads = 128;       // one thread per sample row / TMEM lane
+constexpr uint32_t kTmemCols = 64;  // fp32 accumulator columns (max N = 64)
+
+// shared memory map (bytes)
+constexpr int kW1 = 0;                       // [64 x 32]
+constexpr int kW2 = kW1 + 64 * 32 * 2;       // [16 x 64]
+constexpr int kW3 = kW2 + 16 * 64 * 2;       // [64 x 32]
+constexpr int kW4 = kW3 + 64 * 32 * 2;       // [64 x 64]
+constexpr int kW5 = kW4 + 64 * 64 * 2;       // [16 x 64] (rows 3..15 zero)
+constexpr int kBufA = kW5 + 16 * 64 * 2;     // [128 x 64]
+constexpr int kBufB = kBufA + kTile * 64 * 2;
+constexpr int kBar = kBufB + kTile * 64 * 2; // mbarrier (8 B) + tmem base (4 B)
+constexpr int kSmemBytes = kBar + 16;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {  // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16, issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread i of warp w = lane 32w+i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors -------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N
+__host__ __device__ constexpr uint32_t idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// byte offset of the 16-byte chunk (row r, k-chunk kc) inside an operand with K columns
+__device__ __forceinline__ int chunk_off(int r, int kc, int K) { return (r >> 3) * (K * 16) + kc * 128 + (r & 7) * 16; }
+
+// one GEMM layer: D[128 x N] = A[128 x K] * W[N x K]^T   (K in {16,32,64})
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int K, int N,
+                                            uint32_t bar) {
+    const uint32_t idesc = idesc_f16(kTile, N);
+    const uint32_t sbo = (uint32_t)K * 16;  // (K/8)*128
+    for (int k = 0; k < K / 16; ++k) {
+        const uint64_t da = smem_desc(a_addr + k * 256, 128, sbo);
+        const uint64_t db = smem_desc(w_addr + k * 256, 128, sbo);
+        umma_f16(tmem_d, da, db, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(bar);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// copy a row-major fp32 weight [rows x K] into the interleaved fp16 operand layout (rows_pad rows)
+__device__ __forceinline__ void stage_weight(uint8_t* smem, const float* __restrict__ w, int rows, int rows_pad, int K) {
+    const int kchunks = K / 8;
+    for (int c = threadIdx.x; c < rows_pad * kchunks; c += kThreads) {
+        const int r = c / kchunks, kc = c % kchunks;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < rows) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(w + r * K + kc * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(w + r * K + kc * 8 + 4));
+            v = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
+        }
+        *reinterpret_cast<uint4*>(smem + chunk_off(r, kc, K)) = v;
+    }
+}
+
+__device__ __forceinline__ void sh16(float x, float y, float z, float* e) {  // spherical_harmonics.py:16-42
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    e[0] = 0.28209479177387814f;
+    e[1] = -0.48860251190291987f * y;
+    e[2] = 0.48860251190291987f * z;
+    e[3] = -0.48860251190291987f * x;
+    e[4] = 1.0925484305920792f * xy;
+    e[5] = -1.0925484305920792f * yz;
+    e[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    e[7] = -1.0925484305920792f * xz;
+    e[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    e[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    e[10] = 2.8906114426405538f * xy * z;
+    e[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    e[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    e[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    e[14] = 1.4453057213202769f * z * (x2 - y2);
+    e[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+// hidden-layer epilogue: TMEM [128 x 64] fp32 -> relu -> fp16 -> next operand buffer (K = 64 layout)
+__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, uint8_t* dst, int row) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float v[16];
+        tmem_ld16(tmem_row + g * 16, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        *reinterpret_cast<uint4*>(dst + chunk_off(row, 2 * g, 64)) =
+            make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(dst + chunk_off(row, 2 * g + 1, 64)) =
+            make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+    }
+}
+
+template <typename TEmb>
+__global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
+                                                           ngp_mlp_weights w, float* __restrict__ sigmas,
+                                                           __half* __restrict__ rgbs, int64_t n) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar = smem_u32(smem + kBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBar + 8);
+
+    // ---- one-time setup: weights -> smem, mbarrier, TMEM allocation
+    stage_weight(smem + kW1, w.w1, 64, 64, 32);
+    stage_weight(smem + kW2, w.w2, 16, 16, 64);
+    stage_weight(smem + kW3, w.w3, 64, 64, 32);
+    stage_weight(smem + kW4, w.w4, 64, 64, 64);
+    stage_weight(smem + kW5, w.w5, 3, 16, 64);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's 32 lanes
+    uint32_t phase = 0;
+
+    const uint32_t aA = smem_u32(smem + kBufA), aB = smem_u32(smem + kBufB);
+    const uint32_t aW1 = smem_u32(smem + kW1), aW2 = smem_u32(smem + kW2), aW3 = smem_u32(smem + kW3),
+                   aW4 = smem_u32(smem + kW4), aW5 = smem_u32(smem + kW5);
+
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * kTile + tid;
+        const bool valid = i < n;
+
+        // ---- stage X = emb[i, 0:32] as fp16 into bufA (K = 32 layout)
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (valid) {
+                if constexpr (sizeof(TEmb) == 2) {
+                    v = __ldg(reinterpret_cast<const uint4*>(emb + i * 32) + kc);
+                } else {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8 + 4));
+                    v = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
+                }
+            }
+            *reinterpret_cast<uint4*>(smem + kBufA + chunk_off(tid, kc, 32)) = v;
+        }
+        float dx = 0.f, dy = 0.f, dz = 1.f;
+        if (valid) {
+            dx = dirs[i * 3 + 0];
+            dy = dirs[i * 3 + 1];
+            dz = dirs[i * 3 + 2];
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- layer 1: H1 = relu(X W1^T)                       [128x32]x[32x64]
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tmem_base, aA, aW1, 32, 64, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        epilogue_hidden(tmem_row, smem + kBufB, tid);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- layer 2: h = H1 W2^T                             [128x64]x[64x16]
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tmem_base, aB, aW2, 64, 16, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        {
+            float h[16];
+            tmem_ld16(tmem_row, h);
+            // TruncExp forward on the fp16-rounded h[:,0] (networks.py:22-24, :146)
+            const float h0 = __half2float(__float2half_rn(h[0]));
+            if (valid) sigmas[i] = expf(h0);
+            // rgb-net input X3 = [SH16((d/|d| + 1)/2) | h]  (networks.py:162-164), K = 32 layout in bufA
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            float e[16];
+            sh16((dx * inv + 1.0f) / 2.0f, (dy * inv + 1.0f) / 2.0f, (dz * inv + 1.0f) / 2.0f, e);
+            uint8_t* dst = smem + kBufA;
+            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 0, 32)) =
+                make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
+            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 1, 32)) =
+                make_uint4(pack_h2(e[8], e[9]), pack_h2(e[10], e[11]), pack_h2(e[12], e[13]), pack_h2(e[14], e[15]));
+            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 2, 32)) =
+                make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 3, 32)) =
+                make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- layer 3: H3 = relu(X3 W3^T)                      [128x32]x[32x64]
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tmem_base, aA, aW3, 32, 64, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        epilogue_hidden(tmem_row, smem + kBufB, tid);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- layer 4: H4 = relu(H3 W4^T)                      [128x64]x[64x64]
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tmem_base, aB, aW4, 64, 64, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        epilogue_hidden(tmem_row, smem + kBufA, tid);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- layer 5: rgb = sigmoid(H4 W5^T)                  [128x64]x[64x16(3 used)]
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tmem_base, aA, aW5, 64, 16, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        {
+            float o[16];
+            tmem_ld16(tmem_row, o);
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float oc = __half2float(__float2half_rn(o[c]));
+                    rgbs[i * 3 + c] = __float2half_rn(1.0f / (1.0f + expf(-oc)));
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // bufA / TMEM are reused by the next tile
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <typename TEmb>
+int launch_fwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, float* sigmas, void* rgbs, int64_t n,
+               cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel<TEmb>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) {
+            ngp::set_error("mlp_fwd_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    const int64_t max_ctas = (int64_t)ngp::sm_count() * 4;  // 52 KB smem + 64 TMEM columns per CTA
+    const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
+    mlp_fwd_kernel<TEmb><<<grid, kThreads, kSmemBytes, st>>>((const TEmb*)emb, dirs, *w, sigmas, (__half*)rgbs, n);
+    NGP_LAUNCHED("mlp_fwd_kernel");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ngp_mlp_save_bytes(int64_t n) {
+    (void)n;
+    return 0;  // the backward recomputes the activations from (emb, dirs): nothing is saved
+}
+
+int ngp_mlp_fwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
+                void* rgbs_f16, void* save, int64_t n, void* stream) {
+    (void)save;
+    NGP_REQUIRE(n >= 0, "negative n");
+    NGP_REQUIRE(emb_dtype == NGP_F32 || emb_dtype == NGP_F16, "bad dtype");
+    if (n == 0) return 0;
+    NGP_REQUIRE(emb && dirs && w && sigmas && rgbs_f16, "null pointer");
+    NGP_REQUIRE(w->w1 && w->w2 && w->w3 && w->w4 && w->w5, "null weight pointer");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(emb) & 15) == 0, "emb must be 16-byte aligned");
+    const uintptr_t wal = reinterpret_cast<uintptr_t>(w->w1) | reinterpret_cast<uintptr_t>(w->w2) |
+                          reinterpret_cast<uintptr_t>(w->w3) | reinterpret_cast<uintptr_t>(w->w4) |
+                          reinterpret_cast<uintptr_t>(w->w5);
+    NGP_REQUIRE((wal & 15) == 0, "weights must be 16-byte aligned");
+    cudaStream_t st = ngp::as_stream(stream);
+    if (emb_dtype == NGP_F16) return launch_fwd<__half>(emb, dirs, w, sigmas, rgbs_f16, n, st);
+    return launch_fwd<float>(emb, dirs, w, sigmas, rgbs_f16, n, st);
+}
+
+int ngp_mlp_bwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
+                const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n, void* stream) {
+    (void)emb; (void)emb_dtype; (void)dirs; (void)w; (void)save; (void)dsigmas; (void)drgbs_f16; (void)demb;
+    (void)grad_w; (void)n; (void)stream;
+    ngp::set_error("ngp_mlp_bwd: not implemented yet");
+    return -2;
+}
+
+}  // extern "C"

@@ -1,0 +1,361 @@
+"""GPU parity: every CUDA kernel (called through the C-ABI via taichi_nerfs_b200.ops) against the CPU
+oracle on the same seeded inputs.  Integer/index work and marching are compared bit-exactly; fp paths
+within the tolerance stated next to each assert (north_star: 1e-3 relative for fp16 paths)."""
+import numpy as np
+import pytest
+import torch
+
+from taichi_nerfs_b200.layout import make_hash_layout
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from taichi_nerfs_b200 import ops as o
+    return o
+
+
+# ---- a1 -------------------------------------------------------------------------------------------
+def test_ray_aabb_bit_exact(ops, oracle, rays_factory):
+    o, d = rays_factory(10007, seed=20)
+    d[:50] *= -1
+    d[50:60, 0] = 0.0  # axis-parallel rays (division by zero -> inf, still IEEE)
+    ref = oracle.ray_aabb_intersect(o, d, 0.5)
+    got = N(ops.ray_aabb_intersect(T(o), T(d), 0.5))
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+# ---- a2 -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [
+    dict(scale=0.5, cascades=1, esf=0.0, occ="lego"),
+    dict(scale=0.5, cascades=1, esf=0.0, occ="random"),
+    dict(scale=16.0, cascades=6, esf=1 / 256, occ="random"),
+    dict(scale=2.0, cascades=3, esf=1 / 256, occ="sparse"),
+])
+def test_march_train_bit_exact(ops, oracle, rays_factory, lego_bitfield, cfg):
+    n = 4099
+    rng = np.random.default_rng(21)
+    radius = 1.4 if cfg["scale"] == 0.5 else 3.0
+    o, d = rays_factory(n, seed=21, radius=radius)
+    nbytes = cfg["cascades"] * 128 ** 3 // 8
+    if cfg["occ"] == "lego":
+        bits = lego_bitfield
+    elif cfg["occ"] == "random":
+        bits = rng.integers(0, 256, nbytes, dtype=np.uint8)
+    else:
+        bits = (rng.random(nbytes) < 0.02).astype(np.uint8) * rng.integers(1, 256, nbytes, dtype=np.uint8)
+    hits = oracle.ray_aabb_intersect(o, d, cfg["scale"])
+    noise = rng.random(n, dtype=np.float32)
+    ra, xyzs, dirs, deltas, ts, S = oracle.raymarching_train(o, d, hits, bits, noise, cfg["cascades"], cfg["scale"],
+                                                            cfg["esf"], 128, 1024)
+    from modules.ray_march import raymarching_train
+    g_ra, g_xyzs, g_dirs, g_deltas, g_ts, g_total = raymarching_train(
+        T(o), T(d), T(hits), T(bits), cfg["cascades"], cfg["scale"], cfg["esf"], 128, 1024, noise=T(noise))
+    assert int(g_total) == S
+    assert np.array_equal(N(g_ra), ra)
+    for a, b in ((g_xyzs, xyzs), (g_dirs, dirs), (g_deltas, deltas), (g_ts, ts)):
+        assert np.array_equal(N(a).view(np.uint32), b.view(np.uint32))
+
+
+def test_march_train_empty_and_overflow(ops, oracle, rays_factory, lego_bitfield):
+    n = 512
+    o, d = rays_factory(n, seed=22)
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    noise = np.zeros(n, np.float32)
+    # empty grid -> zero samples
+    empty = np.zeros_like(lego_bitfield)
+    counter, rays_a = ops.raymarching_train_count(T(o), T(d), T(hits), T(empty), T(noise), 1, 0.5, 0.0, 128, 1024)
+    assert N(counter).tolist() == [0, n] and not N(rays_a)[:, 2].any()
+    # capacity smaller than the total: rays that do not fit are dropped as a suffix
+    ra, *_, S = oracle.raymarching_train(o, d, hits, lego_bitfield, noise, 1, 0.5, 0.0, 128, 1024)
+    cap = S // 2
+    tb = T(lego_bitfield)
+    counter, rays_a = ops.raymarching_train_count(T(o), T(d), T(hits), tb, T(noise), 1, 0.5, 0.0, 128, 1024)
+    bufs = [torch.zeros(cap, 3, device=DEV), torch.zeros(cap, 3, device=DEV), torch.zeros(cap, device=DEV),
+            torch.zeros(cap, device=DEV)]
+    ops.raymarching_train_write(T(o), T(d), T(hits), tb, T(noise), 1, 0.5, 0.0, 128, counter, rays_a, *bufs)
+    c = N(counter)
+    g = N(rays_a)
+    assert c[0] <= cap and c[0] == g[:, 2].sum()
+    kept = g[:, 2] > 0
+    assert np.array_equal(g[kept, 2], ra[kept, 2])
+    dropped = (~kept) & (ra[:, 2] > 0)
+    assert dropped.any()
+    assert not kept[np.argmax(dropped):].any()  # dropped rays form a suffix
+
+
+# ---- a3 -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("max_samples", [1, 4, 64])
+def test_march_test_bit_exact(ops, oracle, rays_factory, lego_bitfield, max_samples):
+    n = 3001
+    o, d = rays_factory(n, seed=23)
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    alive = np.random.default_rng(23).permutation(n)[: n // 2].astype(np.int64)
+    h_ref = hits.copy()
+    ri, valid, dl, tt, cnt = oracle.raymarching_test(o, d, h_ref, alive, lego_bitfield, 1, 0.5, 0.0, 128, max_samples)
+    h_gpu = T(hits)
+    A, m = alive.shape[0], max_samples
+    g_ri = torch.zeros(A * m, device=DEV, dtype=torch.long)
+    g_valid = torch.zeros(A * m, device=DEV, dtype=torch.uint8)
+    g_dl = torch.zeros(A * m, device=DEV)
+    g_tt = torch.zeros(A * m, device=DEV)
+    g_cnt = torch.zeros(A, device=DEV, dtype=torch.int32)
+    ops.raymarching_test(T(o), T(d), h_gpu, T(alive), T(lego_bitfield), 1, 0.5, 0.0, 128, m, g_ri, g_valid, g_dl, g_tt, g_cnt)
+    assert np.array_equal(N(g_cnt), cnt)
+    assert np.array_equal(N(g_valid), valid)
+    v = valid.astype(bool)
+    assert np.array_equal(N(g_ri)[v], ri[v])
+    assert np.array_equal(N(g_dl)[v].view(np.uint32), dl[v].view(np.uint32))
+    assert np.array_equal(N(g_tt)[v].view(np.uint32), tt[v].view(np.uint32))
+    assert np.array_equal(N(h_gpu).view(np.uint32), h_ref.view(np.uint32))  # in-place resume points
+
+
+# ---- a4/a5 ----------------------------------------------------------------------------------------
+def _table(rng, lay, half):
+    if half:
+        return ((rng.random(lay.total_param_size, dtype=np.float32) * 2 - 1) * 1e-4).astype(np.float16)
+    return rng.random(lay.total_param_size, dtype=np.float32)
+
+
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("max_res", [1024, 4096])
+@pytest.mark.parametrize("n", [1, 127, 5000])
+def test_hash_fwd_bit_exact(ops, oracle, half, max_res, n):
+    rng = np.random.default_rng(24)
+    lay = make_hash_layout(2 ** 19, 16, 16, max_res, 2)
+    xyz = rng.random((n, 3), dtype=np.float32)
+    xyz[: min(n, 4)] = np.array([[0, 0, 0], [1, 1, 1], [0, 1, 0.5], [1, 0, 1]], np.float32)[: min(n, 4)]
+    table = _table(rng, lay, half)
+    ref = oracle.hash_encode_fwd(xyz, table, lay)
+    got = N(ops.hash_encode_fwd(T(xyz), T(table), lay.as_ctypes(), lay.out_dim))
+    assert got.dtype == ref.dtype and got.shape == ref.shape
+    # identical op order on both sides (no FMA contraction) -> bit exact, fp16 and fp32
+    assert np.array_equal(got.view(np.uint8), ref.view(np.uint8))
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_hash_bwd_matches_oracle(ops, oracle, half):
+    rng = np.random.default_rng(25)
+    lay = make_hash_layout(2 ** 19, 16, 16, 1024, 2)
+    n = 20000
+    # samples along rays: spatially coherent like real marching output (stresses atomic contention)
+    base = rng.random((n // 100, 1, 3), dtype=np.float32) * 0.8 + 0.1
+    xyz = (base + (np.arange(100, dtype=np.float32)[None, :, None] * 0.0015)).reshape(-1, 3).clip(0, 1).astype(np.float32)
+    dout = rng.standard_normal((n, 32)).astype(np.float32)
+    dout[rng.random(n) < 0.1] = 0.0  # zero-gradient samples are skipped (hash_encoder_half.py:210)
+    if half:
+        dout = dout.astype(np.float16)
+    ref = oracle.hash_encode_bwd(xyz, dout, lay)
+    g = torch.zeros(lay.total_param_size, device=DEV)
+    ops.hash_encode_bwd(T(xyz), T(dout), lay.as_ctypes(), g)
+    got = N(g)
+    # fp32 atomics in arbitrary order vs sequential fp32 sums: 1e-3 relative (north_star tolerance)
+    # measured against the per-level gradient magnitude
+    assert np.array_equal(got == 0, ref == 0)
+    np.testing.assert_allclose(got, ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max() * 1e-2)
+
+
+def test_hash_bwd_input_matches_oracle(ops, oracle):
+    rng = np.random.default_rng(26)
+    lay = make_hash_layout(2 ** 19, 16, 16, 1024, 2)
+    n = 3000
+    xyz = rng.random((n, 3), dtype=np.float32)
+    table = rng.standard_normal(lay.total_param_size).astype(np.float32)
+    dout = rng.standard_normal((n, 32)).astype(np.float32)
+    ref = oracle.hash_encode_bwd_input(xyz, table, dout, lay)
+    got = N(ops.hash_encode_bwd_input(T(xyz), T(table), T(dout), lay.as_ctypes()))
+    np.testing.assert_allclose(got, ref, rtol=1e-3, atol=1e-3 * np.abs(ref).max())
+
+
+def test_hash_autograd_modules(oracle):
+    """HashEncoder drop-in modules: forward + backward through torch.autograd."""
+    from modules.hash_encoder import HashEncoder as H32
+    from modules.hash_encoder_half import HashEncoder as H16
+    rng = np.random.default_rng(27)
+    x = rng.random((4000, 3), dtype=np.float32)
+    for cls, half in ((H32, False), (H16, True)):
+        enc = cls(max_params=2 ** 19, levels=16, base_res=16, max_res=1024).to(DEV)
+        lay = make_hash_layout(2 ** 19, 16, 16, 1024, 2)
+        out = enc(T(x))
+        tab = N(enc.hash_table).reshape(-1)
+        ref = oracle.hash_encode_fwd(x, tab.astype(np.float16) if half else tab, lay)
+        assert np.array_equal(N(out).view(np.uint8), ref.view(np.uint8))
+        dout = rng.standard_normal(ref.shape).astype(ref.dtype)
+        out.backward(T(dout))
+        gref = oracle.hash_encode_bwd(x, dout, lay)
+        np.testing.assert_allclose(N(enc.hash_table.grad).reshape(-1), gref, rtol=1e-3, atol=1e-5)
+        assert enc.hash_table.grad.shape == enc.hash_table.shape
+
+
+# ---- a6 -------------------------------------------------------------------------------------------
+def test_dir_encode(ops, oracle):
+    rng = np.random.default_rng(28)
+    d = rng.random((5003, 3), dtype=np.float32)
+    ref = oracle.dir_encode(d)
+    got = N(ops.dir_encode(T(d)))
+    np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-7)  # nvcc may contract a*b+c into fma
+
+
+# ---- a7 -------------------------------------------------------------------------------------------
+def _weights(rng):
+    shapes = [(64, 32), (16, 64), (64, 32), (64, 64), (3, 64)]
+    return [(rng.uniform(-1, 1, s) * np.sqrt(6 / (s[0] + s[1]))).astype(np.float32) for s in shapes]
+
+
+@pytest.mark.parametrize("emb_half", [True, False])
+@pytest.mark.parametrize("n", [1, 128, 1000, 70001])
+def test_mlp_fwd_tcgen05_matches_oracle(ops, oracle, emb_half, n):
+    rng = np.random.default_rng(29)
+    emb = rng.standard_normal((n, 32)).astype(np.float16 if emb_half else np.float32)
+    dirs = rng.standard_normal((n, 3)).astype(np.float32)
+    ws = _weights(rng)
+    sig_ref, rgb_ref = oracle.mlp_fwd(emb, dirs, ws)
+    sig, rgb = ops.mlp_fwd(T(emb), T(dirs), [T(w) for w in ws])
+    sig, rgb = N(sig), N(rgb).astype(np.float32)
+    # fp16 operands / fp32 accumulate on both sides; the tensor core sums K in a different order, so
+    # an fp16-rounded layer output may differ by 1 fp16 ulp: 2e-3 relative on sigma (= exp of an fp16
+    # value around |h|<8 -> 2^-11 * 8 absolute in the exponent), 2e-3 absolute on rgb in [0,1]
+    np.testing.assert_allclose(sig, sig_ref, rtol=8e-3)
+    assert np.abs(rgb - rgb_ref.astype(np.float32)).max() <= 2e-3
+    assert np.median(np.abs(sig - sig_ref) / sig_ref) < 1e-3
+
+
+# ---- a8 -------------------------------------------------------------------------------------------
+def _composite_inputs(rng, n_rays, max_n, dense, half):
+    counts = rng.integers(0, max_n, n_rays)
+    counts[:3] = [0, 1, 33]
+    S = int(counts.sum())
+    rays_a = np.stack([rng.permutation(n_rays), np.cumsum(counts) - counts, counts], 1).astype(np.int32)
+    sig = (rng.random(S) * (60.0 if dense else 3.0)).astype(np.float32)
+    rgbs = rng.random((S, 3)).astype(np.float16 if half else np.float32)
+    deltas = np.full(S, 1.7320508075688772 / 1024 * (20 if dense else 1), np.float32)
+    ts = np.sort(rng.random(S)).astype(np.float32)
+    return rays_a, sig, rgbs, deltas, ts
+
+
+@pytest.mark.parametrize("dense", [False, True])
+@pytest.mark.parametrize("half", [False, True])
+def test_composite_train_fwd_bwd(ops, oracle, dense, half):
+    rng = np.random.default_rng(30)
+    rays_a, sig, rgbs, deltas, ts = _composite_inputs(rng, 700, 300, dense, half)
+    n, S = rays_a.shape[0], sig.shape[0]
+    tot, op, dep, rgb, ws = oracle.composite_train_fwd(sig, rgbs, deltas, ts, rays_a, 1e-4)
+    g = ops.composite_train_fwd(T(sig), T(rgbs), T(deltas), T(ts), T(rays_a), 1e-4)
+    g_tot, g_op, g_dep, g_rgb, g_ws = [N(x) for x in g]
+    # warp prefix products vs sequential products: 1e-5 absolute on O(1) sums
+    np.testing.assert_allclose(g_op, op, atol=2e-5)
+    np.testing.assert_allclose(g_dep, dep, atol=2e-5)
+    np.testing.assert_allclose(g_rgb, rgb, atol=2e-5)
+    np.testing.assert_allclose(g_ws, ws, atol=2e-6)
+    # early-termination point may move by one sample when T crosses 1e-4 within rounding
+    assert np.abs(g_tot.astype(np.int64) - tot).max() <= 1
+    assert (g_tot != tot).mean() < 0.02
+
+    go, gd = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    gr, gw = rng.standard_normal((n, 3)).astype(np.float32), rng.standard_normal(S).astype(np.float32)
+    dsig, drgbs = oracle.composite_train_bwd(go, gd, gr, gw, sig, rgbs, deltas, ts, rays_a, 1e-4)
+    g_dsig, g_drgbs = ops.composite_train_bwd(T(go), T(gd), T(gr), T(gw), T(sig), T(rgbs), T(deltas), T(ts), T(rays_a), 1e-4)
+    g_dsig, g_drgbs = N(g_dsig), N(g_drgbs).astype(np.float32)
+    same_active = g_tot == tot
+    ray_of = np.empty(S, np.int64)
+    for r, s0, c in rays_a:
+        ray_of[s0:s0 + c] = r
+    m = same_active[ray_of]
+    scale = np.abs(dsig).max()
+    assert np.abs(g_dsig[m] - dsig[m]).max() <= 1e-3 * scale
+    tol = 2e-3 if half else 1e-5
+    assert np.abs(g_drgbs[m] - drgbs[m].astype(np.float32)).max() <= tol * max(1.0, np.abs(drgbs).max())
+
+
+def test_volume_renderer_autograd(oracle):
+    from modules.volume_train import VolumeRenderer
+    rng = np.random.default_rng(31)
+    rays_a, sig, rgbs, deltas, ts = _composite_inputs(rng, 300, 120, False, True)
+    vr = VolumeRenderer()
+    s, c = T(sig).requires_grad_(True), T(rgbs).requires_grad_(True)
+    total, opacity, depth, rgb, ws = vr(s, c, T(deltas), T(ts), T(rays_a), 1e-4)
+    tgt = torch.rand_like(rgb)
+    loss = ((rgb + (1 - opacity)[:, None] - tgt) ** 2).mean()
+    loss.backward()
+    n = rays_a.shape[0]
+    g_rgb = N(2 * (rgb + (1 - opacity)[:, None] - tgt) / (3 * n))
+    g_op = -g_rgb.sum(1)
+    dsig, drgbs = oracle.composite_train_bwd(g_op, np.zeros(n, np.float32), g_rgb, np.zeros_like(sig), sig, rgbs,
+                                             deltas, ts, rays_a, 1e-4)
+    assert np.abs(N(s.grad) - dsig).max() <= 1e-3 * np.abs(dsig).max()
+    assert int(total) == int(oracle.composite_train_fwd(sig, rgbs, deltas, ts, rays_a, 1e-4)[0].sum())
+
+
+# ---- a9 -------------------------------------------------------------------------------------------
+def test_composite_test(ops, oracle):
+    rng = np.random.default_rng(32)
+    n_rays, A = 500, 300
+    alive = rng.permutation(n_rays)[:A].astype(np.int64)
+    steps = rng.integers(0, 9, A)
+    pack = np.stack([np.cumsum(steps) - steps, steps], 1).astype(np.int64)
+    S = int(steps.sum())
+    sig = (rng.random(S) * 2000).astype(np.float32)
+    rgbs = rng.random((S, 3)).astype(np.float16)
+    deltas = np.full(S, 1.7320508075688772 / 1024, np.float32)
+    ts = rng.random(S).astype(np.float32)
+    op0 = (rng.random(n_rays) * 0.5).astype(np.float32)
+    r_alive, r_op, r_dep, r_rgb = alive.copy(), op0.copy(), np.zeros(n_rays, np.float32), np.zeros((n_rays, 3), np.float32)
+    oracle.composite_test(sig, rgbs, deltas, ts, pack, r_alive, 1e-4, r_op, r_dep, r_rgb)
+    g_alive, g_op, g_dep, g_rgb = T(alive), T(op0), torch.zeros(n_rays, device=DEV), torch.zeros(n_rays, 3, device=DEV)
+    ops.composite_test(T(sig), T(rgbs), T(deltas), T(ts), T(pack), g_alive, 1e-4, g_op, g_dep, g_rgb)
+    assert np.array_equal(N(g_alive), r_alive)
+    np.testing.assert_allclose(N(g_op), r_op, atol=1e-6)
+    np.testing.assert_allclose(N(g_dep), r_dep, atol=1e-6)
+    np.testing.assert_allclose(N(g_rgb), r_rgb, atol=1e-6)
+
+
+# ---- grid helpers / optimizer -------------------------------------------------------------------------
+def test_packbits_morton_bit_exact(ops, oracle):
+    rng = np.random.default_rng(33)
+    grid = rng.standard_normal(128 ** 3).astype(np.float32)
+    bits = torch.zeros(128 ** 3 // 8, device=DEV, dtype=torch.uint8)
+    ops.packbits(T(grid), 0.25, bits)
+    assert np.array_equal(N(bits), oracle.packbits(grid, 0.25))
+    coords = rng.integers(0, 128, (100003, 3)).astype(np.int32)
+    idx = ops.morton3d(T(coords))
+    assert np.array_equal(N(idx), oracle.morton3d(coords))
+    assert np.array_equal(N(ops.morton3d_invert(idx)), coords)
+
+
+@pytest.mark.parametrize("n", [1000, 11420064 // 8 + 3])
+def test_adam_fused(ops, oracle, n):
+    rng = np.random.default_rng(34)
+    p = rng.standard_normal(n).astype(np.float32)
+    m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    gp, gm, gv = T(p), T(m), T(v)
+    shadow = torch.zeros(n, device=DEV, dtype=torch.float16)
+    found = torch.zeros(1, device=DEV, dtype=torch.int32)
+    for step in range(1, 4):
+        g = (rng.standard_normal(n) * 65536).astype(np.float32)
+        gg = T(g)
+        ops.check_finite(gg, found)
+        ops.adam_step(gp, gg, gm, gv, 1e-2, step, inv_scale=1 / 65536, param_f16=shadow, found_inf=found, zero_grad=True)
+        oracle.adam_step(p, g, m, v, 1e-2, step, inv_scale=1 / 65536)
+        assert not N(gg).any()
+    # same fp32 formula; sqrt/div rounding may differ in the last ulp and nvcc contracts into fma
+    np.testing.assert_allclose(N(gp), p, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(N(gv), v, rtol=2e-6)
+    assert np.array_equal(N(shadow), N(gp).astype(np.float16))
+    # inf -> step skipped
+    before = N(gp).copy()
+    g = T(np.full(n, np.nan, np.float32))
+    ops.check_finite(g, found)
+    assert int(found) == 1
+    ops.adam_step(gp, g, gm, gv, 1e-2, 4, found_inf=found)
+    assert np.array_equal(N(gp), before)

@@ -1,0 +1,433 @@
+"""CPU-only validation of the oracle itself (the reference ships no tests or golden vectors, so the
+oracle is cross-checked against independent numpy / torch restatements, fp64 finite differences and
+algebraic properties)."""
+import numpy as np
+import pytest
+import torch
+
+from taichi_nerfs_b200.layout import make_hash_layout
+
+
+# ------------------------------------------------------------------------------------------------
+# independent numpy restatement of the hash encoder (vectorised over samples, one level at a time)
+def np_hash_encode(xyz, table, lay, half):
+    n = xyz.shape[0]
+    F = lay.feat_dim
+    tab = table.reshape(-1, F)
+    out = np.zeros((n, lay.levels, F), np.float16 if half else np.float32)
+    for l in range(lay.levels):
+        scale = np.float32(lay.scales[l])
+        res = np.uint32(lay.resolutions[l])
+        pos = (xyz * scale).astype(np.float32) + np.float32(0.5)
+        g = np.floor(pos).astype(np.int64).astype(np.uint32)
+        gf = g.astype(np.float16).astype(np.float32) if half else g.astype(np.float32)
+        frac = pos - gf
+        acc = np.zeros((n, F), np.float16 if half else np.float32)
+        for c in range(8):
+            w = np.ones(n, np.float32)
+            p = []
+            for d in range(3):
+                if c & (1 << d):
+                    p.append(g[:, d] + np.uint32(1))
+                    w = w * frac[:, d]
+                else:
+                    p.append(g[:, d])
+                    w = w * (np.float32(1) - frac[:, d])
+            if l < lay.begin_fast_hash_level:
+                h = p[0] + p[1] * res + p[2] * (res * res)
+            else:
+                h = p[0] ^ (p[1] * np.uint32(2654435761)) ^ (p[2] * np.uint32(805459861))
+            idx = lay.offsets[l] + (h % np.uint32(lay.map_sizes[l])).astype(np.int64)
+            prod = w[:, None] * tab[idx].astype(np.float32)
+            if half:
+                acc = (acc.astype(np.float64) + prod.astype(np.float16).astype(np.float64)).astype(np.float16)
+            else:
+                acc = acc + prod
+        out[:, l] = acc
+    return out.reshape(n, -1)
+
+
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("max_res", [1024, 4096])
+def test_hash_fwd_matches_numpy(oracle, half, max_res):
+    rng = np.random.default_rng(1)
+    lay = make_hash_layout(2 ** 19, 16, 16, max_res, 2)
+    n = 2000
+    xyz = rng.random((n, 3), dtype=np.float32)
+    xyz[:8] = np.array([[0, 0, 0], [1, 1, 1], [0, 1, 0.5], [1, 0, 0], [0.5, 0.5, 0.5], [1, 1, 0], [0, 0, 1],
+                        [0.999999, 1e-7, 0.25]], np.float32)
+    if half:
+        table = ((rng.random(lay.total_param_size, dtype=np.float32) * 2 - 1) * 1e-4).astype(np.float16)
+    else:
+        table = rng.random(lay.total_param_size, dtype=np.float32)
+    with np.errstate(over="ignore"):
+        ref = np_hash_encode(xyz, table, lay, half)
+    got = oracle.hash_encode_fwd(xyz, table, lay)
+    assert got.dtype == ref.dtype
+    if half:
+        assert np.array_equal(got.view(np.uint16), ref.view(np.uint16))
+    else:
+        np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-7)  # summation order of 8 terms
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_hash_bwd_is_adjoint_of_fwd(oracle, half):
+    """<encode(table), dout> == <table, bwd(dout)> (the encoder is linear in the table)."""
+    rng = np.random.default_rng(2)
+    lay = make_hash_layout(2 ** 19, 16, 16, 1024, 2)
+    n = 3000
+    xyz = rng.random((n, 3), dtype=np.float32)
+    table = rng.standard_normal(lay.total_param_size).astype(np.float32)
+    dout = rng.standard_normal((n, 32)).astype(np.float32)
+    if half:
+        dout = dout.astype(np.float16)
+    out = oracle.hash_encode_fwd(xyz, table, lay).astype(np.float64)  # fp32 forward = exact linear map
+    grad = oracle.hash_encode_bwd(xyz, dout, lay)
+    lhs = float((out * dout.astype(np.float64)).sum())
+    rhs = float((table.astype(np.float64) * grad.astype(np.float64)).sum())
+    assert abs(lhs - rhs) <= 2e-4 * max(abs(lhs), 1.0)
+
+
+def test_hash_bwd_input_matches_finite_difference(oracle):
+    rng = np.random.default_rng(3)
+    lay = make_hash_layout(2 ** 14, 4, 4, 32, 2)  # coarse grid: FD stays inside one cell
+    n = 64
+    xyz = (rng.random((n, 3)) * 0.9 + 0.05).astype(np.float32)
+    table = rng.standard_normal(lay.total_param_size).astype(np.float32)
+    dout = rng.standard_normal((n, lay.out_dim)).astype(np.float32)
+    dx = oracle.hash_encode_bwd_input(xyz, table, dout, lay)
+    eps = 1e-3
+    for d in range(3):
+        xp, xm = xyz.copy(), xyz.copy()
+        xp[:, d] += eps
+        xm[:, d] -= eps
+        fd = ((oracle.hash_encode_fwd(xp, table, lay).astype(np.float64) -
+               oracle.hash_encode_fwd(xm, table, lay).astype(np.float64)) * dout).sum(1) / (xp[:, d] - xm[:, d])
+        ok = np.isclose(dx[:, d], fd, rtol=5e-2, atol=5e-2)
+        assert ok.mean() > 0.8  # samples whose +-eps straddles a cell boundary are excluded
+
+
+# ------------------------------------------------------------------------------------------------
+def test_aabb_matches_numpy(oracle, rays_factory):
+    o, d = rays_factory(4096, seed=4)
+    d[:10] *= -1  # rays pointing away
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    inv = (1.0 / d).astype(np.float32)
+    tmin = ((-0.5 - o) * inv).astype(np.float32)
+    tmax = ((0.5 - o) * inv).astype(np.float32)
+    t1 = np.minimum(tmin, tmax).max(1)
+    t2 = np.maximum(tmin, tmax).min(1)
+    ref = np.where((t2 > 0)[:, None], np.stack([np.maximum(t1, np.float32(0.01)), t2], 1), -1.0).astype(np.float32)
+    assert np.array_equal(hits, ref)
+
+
+def test_march_train_properties(oracle, lego_bitfield, rays_factory):
+    n = 2048
+    o, d = rays_factory(n, seed=5)
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    noise = np.random.default_rng(5).random(n, dtype=np.float32)
+    rays_a, xyzs, dirs, deltas, ts, S = oracle.raymarching_train(o, d, hits, lego_bitfield, noise, 1, 0.5, 0.0, 128, 1024)
+    assert S == rays_a[:, 2].sum() and xyzs.shape == (S, 3)
+    assert np.array_equal(rays_a[:, 0], np.arange(n))
+    assert np.array_equal(rays_a[:, 1], np.cumsum(rays_a[:, 2]) - rays_a[:, 2])
+    # every sample lies in an occupied cell, inside [t1, t2), on its ray, with the constant Lego step
+    ray_of = np.repeat(np.arange(n), rays_a[:, 2])
+    assert np.allclose(xyzs, o[ray_of] + ts[:, None] * d[ray_of], atol=1e-6)
+    assert np.all(ts < hits[ray_of, 1]) and np.all(ts >= hits[ray_of, 0])
+    assert np.all(deltas == np.float32(1.7320508075688772 / 1024))
+    cell = np.clip(0.5 * (xyzs / 0.5 + 1) * 128, 0, 127).astype(np.uint32)
+    mort = oracle.morton3d(cell.astype(np.int32)).astype(np.int64)
+    bits = np.unpackbits(lego_bitfield, bitorder="little")
+    assert bits[mort].all()
+    # statistics of the trained Lego grid from SURVEY.md §8d (independent numpy march): ~35 % of rays
+    # have samples, ~22 samples/ray on average
+    assert 0.25 < (rays_a[:, 2] > 0).mean() < 0.45
+    assert 15 < S / n < 30
+    # ts strictly increasing within a ray
+    starts = rays_a[:, 1]
+    inc = np.diff(ts) > 0
+    boundary = np.zeros(S - 1, bool)
+    boundary[starts[1:][(starts[1:] > 0) & (starts[1:] < S)] - 1] = True
+    assert np.all(inc | boundary)
+
+
+def test_march_full_grid_counts(oracle, rays_factory):
+    """Fully occupied grid: every step of the chord is a sample => n = number of dt steps in [t1, t2)."""
+    n = 256
+    o, d = rays_factory(n, seed=6)
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    full = np.full(128 ** 3 // 8, 255, np.uint8)
+    noise = np.zeros(n, np.float32)
+    rays_a, xyzs, dirs, deltas, ts, S = oracle.raymarching_train(o, d, hits, full, noise, 1, 0.5, 0.0, 128, 1024)
+    dt = np.float32(1.7320508075688772 / 1024)
+    for r in range(0, n, 17):
+        t, cnt = hits[r, 0], 0
+        while 0 <= t < hits[r, 1] and cnt < 1024:
+            t = np.float32(t + dt)
+            cnt += 1
+        assert cnt == rays_a[r, 2]
+
+
+def test_march_capacity_overflow(oracle, lego_bitfield, rays_factory):
+    import ctypes as C
+    n = 512
+    o, d = rays_factory(n, seed=7)
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    noise = np.zeros(n, np.float32)
+    rays_a, *_, S = oracle.raymarching_train(o, d, hits, lego_bitfield, noise, 1, 0.5, 0.0, 128, 1024)
+    cap = S // 2
+    L = oracle.lib()
+    counter = np.array([S, n], np.int32)
+    ra = rays_a.copy()
+    bufs = [np.zeros((cap, 3), np.float32), np.zeros((cap, 3), np.float32), np.zeros(cap, np.float32), np.zeros(cap, np.float32)]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = L.ngp_raymarching_train_write_cpu(p(o), p(d), p(hits), p(lego_bitfield), p(noise), 1, 128, C.c_float(0.5),
+                                           C.c_float(0.0), p(counter), p(ra), *[p(b) for b in bufs],
+                                           C.c_int64(n), C.c_int64(cap))
+    assert rc == 0
+    assert counter[0] <= cap and counter[0] == ra[:, 2].sum()
+    kept = ra[:, 2] > 0
+    assert np.array_equal(ra[kept, 2], rays_a[kept, 2])
+
+
+def test_march_test_matches_train_samples(oracle, lego_bitfield, rays_factory):
+    """Chunked test-time marching visits exactly the samples of a noise-free training march."""
+    n = 300
+    o, d = rays_factory(n, seed=8)
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    noise = np.zeros(n, np.float32)
+    rays_a, xyzs, dirs, deltas, ts, S = oracle.raymarching_train(o, d, hits, lego_bitfield, noise, 1, 0.5, 0.0, 128, 1024)
+    h = hits.copy()
+    alive = np.arange(n, dtype=np.int64)
+    got = [[] for _ in range(n)]
+    for it in range(400):
+        if alive.size == 0:
+            break
+        ri, valid, dl, tt, cnt = oracle.raymarching_test(o, d, h, alive, lego_bitfield, 1, 0.5, 0.0, 128, 4)
+        for k, r in enumerate(alive):
+            got[r].extend(tt[k * 4:k * 4 + cnt[k]].tolist())
+        alive = alive[cnt > 0]
+    for r in range(n):
+        ref = ts[rays_a[r, 1]:rays_a[r, 1] + rays_a[r, 2]]
+        assert np.array_equal(np.asarray(got[r], np.float32), ref), r
+
+
+# ------------------------------------------------------------------------------------------------
+def test_sh_matches_closed_form(oracle):
+    rng = np.random.default_rng(9)
+    d = rng.standard_normal((100, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    out = oracle.dir_encode(d.astype(np.float32))
+    x, y, z = d.T
+    assert np.allclose(out[:, 0], 0.28209479177387814)
+    assert np.allclose(out[:, 2], 0.48860251190291987 * z, atol=1e-6)
+    assert np.allclose(out[:, 6], 0.94617469575755997 * z * z - 0.31539156525251999, atol=1e-6)
+    assert np.allclose(out[:, 15], 0.59004358992664352 * x * (-x * x + 3 * y * y), atol=1e-6)
+    # real SH of degree l are orthonormal-ish: sum_m Y_lm^2 = (2l+1)/(4 pi) on the unit sphere
+    for l, (a, b) in enumerate([(0, 1), (1, 4), (4, 9), (9, 16)]):
+        assert np.allclose((out[:, a:b] ** 2).sum(1), (2 * l + 1) / (4 * np.pi), atol=1e-5)
+
+
+def _torch_mlp_reference(emb, dirs, ws):
+    """Independent torch restatement of NGP.forward's network part under autocast semantics
+    (fp16 operands, fp32 accumulate, fp16 layer outputs), modules/networks.py:136-166."""
+    h16 = lambda t: t.half().float()
+    W = [h16(torch.from_numpy(w)) for w in ws]
+    e = h16(torch.from_numpy(emb.astype(np.float32)))
+    h1 = torch.relu(h16(e @ W[0].T))
+    h = h16(h1 @ W[1].T)
+    sigma = torch.exp(h[:, 0])
+    d = torch.from_numpy(dirs)
+    d = d / d.norm(dim=1, keepdim=True)
+    d = (d + 1) / 2
+    x, y, z = d.unbind(1)
+    sh = torch.from_numpy(np.zeros((len(d), 16), np.float32))
+    from oracle import oracle as O
+    sh = torch.from_numpy(O.dir_encode(d.numpy()))
+    x3 = torch.cat([h16(sh), h], 1)
+    h3 = torch.relu(h16(x3 @ W[2].T))
+    h4 = torch.relu(h16(h3 @ W[3].T))
+    o = h16(h4 @ W[4].T)
+    rgb = h16(torch.sigmoid(o))
+    return sigma.numpy(), rgb.numpy()
+
+
+def _rand_weights(rng):
+    shapes = [(64, 32), (16, 64), (64, 32), (64, 64), (3, 64)]
+    return [(rng.uniform(-1, 1, s) * np.sqrt(6 / (s[0] + s[1]))).astype(np.float32) for s in shapes]
+
+
+def test_mlp_fwd_matches_torch(oracle):
+    rng = np.random.default_rng(10)
+    n = 512
+    emb = rng.standard_normal((n, 32)).astype(np.float16)
+    dirs = rng.standard_normal((n, 3)).astype(np.float32)
+    ws = _rand_weights(rng)
+    sig, rgb = oracle.mlp_fwd(emb, dirs, ws)
+    sig_ref, rgb_ref = _torch_mlp_reference(emb, dirs, ws)
+    # fp16 rounding of every layer output makes 1-ulp(fp16) flips possible when the fp32 dot
+    # product is summed in a different order
+    np.testing.assert_allclose(sig, sig_ref, rtol=4e-3)
+    np.testing.assert_allclose(rgb.astype(np.float32), rgb_ref, atol=2e-3)
+
+
+def test_mlp_bwd_matches_torch_autograd(oracle):
+    """fp32 autograd through the same fp16-rounded forward values (straight-through on the rounding)."""
+    rng = np.random.default_rng(11)
+    n = 256
+    emb = (rng.standard_normal((n, 32)) * 0.5).astype(np.float16)
+    dirs = rng.standard_normal((n, 3)).astype(np.float32)
+    ws = _rand_weights(rng)
+    dsig = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    drgb = (rng.standard_normal((n, 3)) * 0.1).astype(np.float16)
+    demb, gw = oracle.mlp_bwd(emb, dirs, ws, dsig, drgb)
+
+    W = [torch.from_numpy(w).half().float().requires_grad_(True) for w in ws]
+    e = torch.from_numpy(emb.astype(np.float32)).requires_grad_(True)
+    h1 = torch.relu(e @ W[0].T)
+    h = h1 @ W[1].T
+    sigma = torch.exp(h[:, 0])
+    d = torch.from_numpy(dirs)
+    d = (d / d.norm(dim=1, keepdim=True) + 1) / 2
+    sh = torch.from_numpy(oracle.dir_encode(d.numpy()))
+    h3 = torch.relu(torch.cat([sh, h], 1) @ W[2].T)
+    h4 = torch.relu(h3 @ W[3].T)
+    rgb = torch.sigmoid(h4 @ W[4].T)
+    loss = (sigma * torch.from_numpy(dsig)).sum() + (rgb * torch.from_numpy(drgb.astype(np.float32))).sum()
+    loss.backward()
+    ref_gw = np.concatenate([w.grad.numpy().reshape(-1) for w in W])
+    scale = np.abs(ref_gw).max()
+    assert np.abs(gw - ref_gw).max() < 2e-2 * scale
+    ref_de = e.grad.numpy()
+    assert np.abs(demb.astype(np.float32) - ref_de).max() < 2e-2 * np.abs(ref_de).max()
+
+
+# ------------------------------------------------------------------------------------------------
+def _composite_inputs(rng, n_rays=64, max_n=80, dense=False):
+    counts = rng.integers(0, max_n, n_rays)
+    counts[0] = 0
+    S = int(counts.sum())
+    rays_a = np.stack([rng.permutation(n_rays), np.cumsum(counts) - counts, counts], 1).astype(np.int32)
+    sig = (rng.random(S) * (40.0 if dense else 3.0)).astype(np.float32)
+    rgbs = rng.random((S, 3)).astype(np.float32)
+    deltas = np.full(S, 1.7320508075688772 / 1024, np.float32) * (20 if dense else 1)
+    ts = np.sort(rng.random(S)).astype(np.float32)
+    return rays_a, sig, rgbs, deltas, ts
+
+
+def _np_composite(rays_a, sig, rgbs, deltas, ts, thr):
+    n = rays_a.shape[0]
+    op, dep, rgb, ws = np.zeros(n), np.zeros(n), np.zeros((n, 3)), np.zeros(sig.shape[0])
+    for ray, start, N in rays_a:
+        T = 1.0
+        for s in range(start, start + N):
+            if T > thr:
+                a = 1 - np.exp(-float(sig[s]) * float(deltas[s]))
+                w = a * T
+                rgb[ray] += w * rgbs[s]
+                dep[ray] += w * ts[s]
+                op[ray] += w
+                ws[s] = w
+                T *= 1 - a
+    return op, dep, rgb, ws
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_composite_fwd_matches_numpy(oracle, dense):
+    rng = np.random.default_rng(12)
+    rays_a, sig, rgbs, deltas, ts = _composite_inputs(rng, dense=dense)
+    tot, op, dep, rgb, ws = oracle.composite_train_fwd(sig, rgbs, deltas, ts, rays_a, 1e-4)
+    rop, rdep, rrgb, rws = _np_composite(rays_a, sig, rgbs, deltas, ts, 1e-4)
+    np.testing.assert_allclose(op, rop, atol=2e-6)
+    np.testing.assert_allclose(dep, rdep, atol=2e-6)
+    np.testing.assert_allclose(rgb, rrgb, atol=2e-6)
+    np.testing.assert_allclose(ws, rws, atol=2e-6)
+    if dense:
+        assert (tot < rays_a[np.argsort(rays_a[:, 0]), 2]).any()  # early termination exercised
+
+
+def test_composite_bwd_matches_finite_difference(oracle):
+    rng = np.random.default_rng(13)
+    rays_a, sig, rgbs, deltas, ts = _composite_inputs(rng, n_rays=12, max_n=20)
+    deltas = deltas * 30
+    n, S = rays_a.shape[0], sig.shape[0]
+    go, gd, gr, gw = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal((n, 3)), rng.standard_normal(S)
+
+    def loss(sig_, rgbs_):
+        op, dep, rgb, ws = _np_composite(rays_a, sig_, rgbs_, deltas, ts, 1e-4)
+        return (op * go).sum() + (dep * gd).sum() + (rgb * gr).sum() + (ws * gw).sum()
+
+    dsig, drgbs = oracle.composite_train_bwd(go, gd, gr, gw, sig, rgbs, deltas, ts, rays_a, 1e-4)
+    eps = 1e-4
+    for s in range(0, S, max(1, S // 40)):
+        sp, sm = sig.astype(np.float64).copy(), sig.astype(np.float64).copy()
+        sp[s] += eps
+        sm[s] -= eps
+        fd = (loss(sp, rgbs) - loss(sm, rgbs)) / (2 * eps)
+        assert abs(fd - dsig[s]) < 1e-4 * max(1.0, abs(fd)), s
+        for c in range(3):
+            rp, rm = rgbs.astype(np.float64).copy(), rgbs.astype(np.float64).copy()
+            rp[s, c] += eps
+            rm[s, c] -= eps
+            fd = (loss(sig, rp) - loss(sig, rm)) / (2 * eps)
+            assert abs(fd - drgbs[s, c]) < 1e-5 * max(1.0, abs(fd))
+
+
+def test_composite_test_equals_train_when_chunked(oracle):
+    """Accumulating chunks with composite_test reproduces the training compositing (no early stop)."""
+    rng = np.random.default_rng(14)
+    rays_a, sig, rgbs, deltas, ts = _composite_inputs(rng, n_rays=40, max_n=50)
+    rays_a[:, 0] = np.arange(40)
+    tot, op, dep, rgb, ws = oracle.composite_train_fwd(sig, rgbs, deltas, ts, rays_a, 0.0)
+    n = 40
+    opacity, depth, out = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+    done = np.zeros(n, np.int64)
+    chunk = 7
+    for it in range(10):
+        alive = np.arange(n, dtype=np.int64)
+        steps = np.minimum(chunk, rays_a[:, 2] - done)
+        pack = np.stack([rays_a[:, 1] + done, steps], 1).astype(np.int64)
+        oracle.composite_test(sig, rgbs, deltas, ts, pack, alive, 0.0, opacity, depth, out)
+        done += steps
+    np.testing.assert_allclose(opacity, op, atol=1e-5)
+    np.testing.assert_allclose(out, rgb, atol=1e-5)
+    np.testing.assert_allclose(depth, dep, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_packbits_and_morton(oracle):
+    rng = np.random.default_rng(15)
+    grid = rng.standard_normal(4096).astype(np.float32)
+    bits = oracle.packbits(grid, 0.1)
+    assert np.array_equal(bits, np.packbits(grid > 0.1, bitorder="little"))
+    coords = rng.integers(0, 128, (1000, 3)).astype(np.int32)
+    idx = oracle.morton3d(coords)
+    assert np.array_equal(oracle.morton3d_invert(idx), coords)
+    assert idx.min() >= 0 and idx.max() < 128 ** 3
+    assert oracle.morton3d(np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [3, 0, 0]], np.int32)).tolist() == [1, 2, 4, 9]
+
+
+def test_adam_matches_torch(oracle):
+    rng = np.random.default_rng(16)
+    n = 1000
+    p0 = rng.standard_normal(n).astype(np.float32)
+    p = p0.copy()
+    m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    tp = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([tp], lr=1e-2, eps=1e-15)
+    shadow = np.zeros(n, np.float16)
+    for step in range(1, 6):
+        g = rng.standard_normal(n).astype(np.float32)
+        tp.grad = torch.from_numpy(g.copy())
+        opt.step()
+        gs = (g * 65536).astype(np.float32)
+        oracle.adam_step(p, gs, m, v, 1e-2, step, inv_scale=1.0 / 65536, param_f16=shadow, zero_grad=True)
+        assert not gs.any()
+    np.testing.assert_allclose(p, tp.detach().numpy(), rtol=1e-5, atol=1e-7)
+    assert np.array_equal(shadow, p.astype(np.float16))
+    # inf skip
+    before = p.copy()
+    g = np.full(n, np.inf, np.float32)
+    assert oracle.check_finite(g) == 1
+    oracle.adam_step(p, g, m, v, 1e-2, 6, found_inf=1)
+    assert np.array_equal(p, before)
