@@ -27,16 +27,35 @@ constexpr int kTile = 128;          // samples per tile == UMMA M
 constexpr int kThreads = 128;       // one thread per sample row / TMEM lane
 constexpr uint32_t kTmemCols = 64;  // fp32 accumulator columns (max N = 64)
 
-// shared memory map (bytes)
+// shared memory map (bytes).  Weights first (shared by both kernels), then activation buffers.
 constexpr int kW1 = 0;                       // [64 x 32]
 constexpr int kW2 = kW1 + 64 * 32 * 2;       // [16 x 64]
 constexpr int kW3 = kW2 + 16 * 64 * 2;       // [64 x 32]
 constexpr int kW4 = kW3 + 64 * 32 * 2;       // [64 x 64]
 constexpr int kW5 = kW4 + 64 * 64 * 2;       // [16 x 64] (rows 3..15 zero)
-constexpr int kBufA = kW5 + 16 * 64 * 2;     // [128 x 64]
-constexpr int kBufB = kBufA + kTile * 64 * 2;
-constexpr int kBar = kBufB + kTile * 64 * 2; // mbarrier (8 B) + tmem base (4 B)
+constexpr int kAct = kW5 + 16 * 64 * 2;      // 20480
+constexpr int kB64 = kTile * 64 * 2;         // one [128 x 64] fp16 operand buffer
+constexpr int kB32 = kTile * 32 * 2;
+constexpr int kB16 = kTile * 16 * 2;
+// forward kernel: two ping-pong buffers
+constexpr int kBufA = kAct;
+constexpr int kBufB = kBufA + kB64;
+constexpr int kBar = kBufB + kB64;           // mbarrier (8 B) + tmem base (4 B)
 constexpr int kSmemBytes = kBar + 16;
+// backward kernel: every activation of the recomputed forward stays resident
+constexpr int kE = kAct;                     // X = emb            [128 x 32]
+constexpr int kH1 = kE + kB32;               // relu(X W1^T)       [128 x 64]   (later: dH1)
+constexpr int kX3 = kH1 + kB64;              // [SH | h]           [128 x 32]
+constexpr int kH3 = kX3 + kB32;              // relu(X3 W3^T)      [128 x 64]   (later: dH1)
+constexpr int kH4 = kH3 + kB64;              // relu(H3 W4^T)      [128 x 64]   (later: dH3)
+constexpr int kDH4 = kH4 + kB64;             // dL/dH4             [128 x 64]
+constexpr int kDO = kDH4 + kB64;             // dL/do (3 of 16)    [128 x 16]
+constexpr int kDH = kDO + kB16;              // dL/dh              [128 x 16]
+constexpr int kBarBwd = kDH + kB16;
+constexpr int kSmemBytesBwd = kBarBwd + 16;  // 110,608 B -> 2 CTAs / SM
+// TMEM columns of the backward kernel: per-tile accumulator + persistent weight-gradient accumulators
+constexpr uint32_t kTmemColsBwd = 256;
+constexpr uint32_t kColDW4 = 64, kColDW1 = 128, kColDW3 = 160, kColDW2T = 192, kColDW5T = 208;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,8 +130,7 @@ __host__ __device__ constexpr uint32_t idesc_f16(int m, int n) {
 __device__ __forceinline__ int chunk_off(int r, int kc, int K) { return (r >> 3) * (K * 16) + kc * 128 + (r & 7) * 16; }
 
 // one GEMM layer: D[128 x N] = A[128 x K] * W[N x K]^T   (K in {16,32,64})
-__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int K, int N,
-                                            uint32_t bar) {
+__device__ __forceinline__ void issue_layer_mma(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int K, int N) {
     const uint32_t idesc = idesc_f16(kTile, N);
     const uint32_t sbo = (uint32_t)K * 16;  // (K/8)*128
     for (int k = 0; k < K / 16; ++k) {
@@ -120,6 +138,10 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, ui
         const uint64_t db = smem_desc(w_addr + k * 256, 128, sbo);
         umma_f16(tmem_d, da, db, idesc, k > 0 ? 1u : 0u);
     }
+}
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int K, int N,
+                                            uint32_t bar) {
+    issue_layer_mma(tmem_d, a_addr, w_addr, K, N);
     umma_commit(bar);
 }
 
@@ -339,6 +361,307 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restric
     if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// =====================================================================================================
+// Backward.  Replaces the autograd graph of the five nn.Linear layers (cuBLAS dX + dW GEMMs), ReLU /
+// Sigmoid / TruncExp backward (modules/networks.py:26-30) under autocast.  Per 128-sample tile:
+//   1. recompute the forward activations into shared memory (nothing was saved by the forward);
+//   2. chain  dO -> dH4 -> dH3 -> dX3 -> dH -> dH1 -> dE  with  dX = dY * W  as tcgen05 MMAs whose B
+//      operand is the SAME shared-memory weight copy read MN-major (i.e. transposed by descriptor);
+//   3. weight gradients  dW = dY^T * X  as M=64 MMAs with K = the 128 samples of the tile, both operands
+//      read MN-major from the activation buffers, accumulated in TMEM across ALL tiles of the persistent
+//      CTA and flushed once at the end with fp32 atomics (9,408 per CTA).
+// Gradient operands of invalid (tail) rows are zero, so they do not contribute to dW.
+
+// generic GEMM issue: operand = (start address, LBO, SBO, bytes to advance per 16-wide K step)
+struct Operand {
+    uint32_t addr, lbo, sbo, kstep;
+};
+// operand stored as [row][K cols] (row-block stride K*16 B) and consumed K-major (rows = M or N)
+__device__ __forceinline__ Operand op_kmajor(uint32_t addr, int K) { return {addr, 128u, (uint32_t)K * 16u, 256u}; }
+// the same storage consumed MN-major: MN = the stored columns, K = the stored rows
+__device__ __forceinline__ Operand op_mnmajor(uint32_t addr, int K) { return {addr, (uint32_t)K * 16u, 128u, (uint32_t)K * 32u}; }
+
+__host__ __device__ constexpr uint32_t idesc_full(int m, int n, int a_mn, int b_mn) {
+    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const Operand& a, const Operand& b, int ksteps,
+                                           uint32_t idesc, bool accumulate) {
+    for (int k = 0; k < ksteps; ++k) {
+        const uint64_t da = smem_desc(a.addr + k * a.kstep, a.lbo, a.sbo);
+        const uint64_t db = smem_desc(b.addr + k * b.kstep, b.lbo, b.sbo);
+        umma_f16(tmem_d, da, db, idesc, (accumulate || k > 0) ? 1u : 0u);
+    }
+}
+
+// backward hidden epilogue: TMEM [128 x 64] fp32 -> fp16, masked by relu'(act) where `act` holds the
+// post-ReLU forward activation of this thread's row -> dst (K = 64 layout).  dst may alias act.
+__device__ __forceinline__ void epilogue_relu_bwd(uint32_t tmem_row, const uint8_t* act, uint8_t* dst, int row) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float v[16];
+        tmem_ld16(tmem_row + g * 16, v);
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+            const uint4 a = *reinterpret_cast<const uint4*>(act + chunk_off(row, 2 * g + hlf, 64));
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __half2 ah = *reinterpret_cast<const __half2*>(&aw[j]);
+                const float m0 = __low2float(ah) > 0.0f ? v[hlf * 8 + 2 * j] : 0.0f;
+                const float m1 = __high2float(ah) > 0.0f ? v[hlf * 8 + 2 * j + 1] : 0.0f;
+                o[j] = pack_h2(m0, m1);
+            }
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 2 * g + hlf, 64)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+template <typename TEmb>
+__global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
+                                                           ngp_mlp_weights w, const float* __restrict__ dsigmas,
+                                                           const __half* __restrict__ drgbs, TEmb* __restrict__ demb,
+                                                           float* __restrict__ grad_w, int64_t n) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar = smem_u32(smem + kBarBwd);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBarBwd + 8);
+
+    stage_weight(smem + kW1, w.w1, 64, 64, 32);
+    stage_weight(smem + kW2, w.w2, 16, 16, 64);
+    stage_weight(smem + kW3, w.w3, 64, 64, 32);
+    stage_weight(smem + kW4, w.w4, 64, 64, 64);
+    stage_weight(smem + kW5, w.w5, 3, 16, 64);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemColsBwd);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+
+    const uint32_t aW1 = smem_u32(smem + kW1), aW2 = smem_u32(smem + kW2), aW3 = smem_u32(smem + kW3),
+                   aW4 = smem_u32(smem + kW4), aW5 = smem_u32(smem + kW5);
+    const uint32_t aE = smem_u32(smem + kE), aH1 = smem_u32(smem + kH1), aX3 = smem_u32(smem + kX3),
+                   aH3 = smem_u32(smem + kH3), aH4 = smem_u32(smem + kH4), aDH4 = smem_u32(smem + kDH4),
+                   aDO = smem_u32(smem + kDO), aDH = smem_u32(smem + kDH);
+
+#define NGP_ROUND(ISSUE)                       \
+    fence_proxy_async();                       \
+    tc_fence_before();                         \
+    __syncthreads();                           \
+    if (tid == 0) {                            \
+        tc_fence_after();                      \
+        ISSUE;                                 \
+        umma_commit(bar);                      \
+    }                                          \
+    mbar_wait(bar, phase);                     \
+    phase ^= 1;                                \
+    tc_fence_after();
+
+    bool first = true;  // first tile of this CTA: weight-gradient accumulators start from zero
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * kTile + tid;
+        const bool valid = i < n;
+
+        // ================= forward recompute =================
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (valid) {
+                if constexpr (sizeof(TEmb) == 2) {
+                    v = __ldg(reinterpret_cast<const uint4*>(emb + i * 32) + kc);
+                } else {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8 + 4));
+                    v = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
+                }
+            }
+            *reinterpret_cast<uint4*>(smem + kE + chunk_off(tid, kc, 32)) = v;
+        }
+        float dx = 0.f, dy = 0.f, dz = 1.f, dsig = 0.f, dr[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+            dx = dirs[i * 3 + 0];
+            dy = dirs[i * 3 + 1];
+            dz = dirs[i * 3 + 2];
+            dsig = dsigmas[i];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dr[c] = __half2float(drgbs[i * 3 + c]);
+        }
+        NGP_ROUND(issue_layer_mma(tmem_base, aE, aW1, 32, 64))          // H1 = relu(E W1^T)
+        epilogue_hidden(tmem_row, smem + kH1, tid);
+        NGP_ROUND(issue_layer_mma(tmem_base, aH1, aW2, 64, 16))         // h = H1 W2^T
+        float h0;
+        {
+            float h[16];
+            tmem_ld16(tmem_row, h);
+            h0 = __half2float(__float2half_rn(h[0]));
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            float e[16];
+            sh16((dx * inv + 1.0f) / 2.0f, (dy * inv + 1.0f) / 2.0f, (dz * inv + 1.0f) / 2.0f, e);
+            uint8_t* dst = smem + kX3;
+            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 0, 32)) =
+                make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
+            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 1, 32)) =
+                make_uint4(pack_h2(e[8], e[9]), pack_h2(e[10], e[11]), pack_h2(e[12], e[13]), pack_h2(e[14], e[15]));
+            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 2, 32)) =
+                make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 3, 32)) =
+                make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
+        }
+        NGP_ROUND(issue_layer_mma(tmem_base, aX3, aW3, 32, 64))         // H3 = relu(X3 W3^T)
+        epilogue_hidden(tmem_row, smem + kH3, tid);
+        NGP_ROUND(issue_layer_mma(tmem_base, aH3, aW4, 64, 64))         // H4 = relu(H3 W4^T)
+        epilogue_hidden(tmem_row, smem + kH4, tid);
+        NGP_ROUND(issue_layer_mma(tmem_base, aH4, aW5, 64, 16))         // o = H4 W5^T
+        {
+            // dL/do = dL/drgb * rgb (1 - rgb), rounded to fp16 like the autocast graph
+            float o[16];
+            tmem_ld16(tmem_row, o);
+            float d_o[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float oc = __half2float(__float2half_rn(o[c]));
+                const float rgb = __half2float(__float2half_rn(1.0f / (1.0f + expf(-oc))));
+                d_o[c] = dr[c] * rgb * (1.0f - rgb);
+            }
+            *reinterpret_cast<uint4*>(smem + kDO + chunk_off(tid, 0, 16)) =
+                make_uint4(pack_h2(d_o[0], d_o[1]), pack_h2(d_o[2], 0.0f), 0u, 0u);
+            *reinterpret_cast<uint4*>(smem + kDO + chunk_off(tid, 1, 16)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+
+        // ================= backward =================
+        // R1: dH4pre = dO W5 ;  dW5^T += H4^T dO
+        NGP_ROUND(
+            issue_gemm(tmem_base, op_kmajor(aDO, 16), op_mnmajor(aW5, 64), 1, idesc_full(128, 64, 0, 1), false);
+            issue_gemm(tmem_base + kColDW5T, op_mnmajor(aH4, 64), op_mnmajor(aDO, 16), 8, idesc_full(64, 16, 1, 1), !first))
+        epilogue_relu_bwd(tmem_row, smem + kH4, smem + kDH4, tid);
+        // R2: dH3pre = dH4 W4 ;  dW4 += dH4^T H3
+        NGP_ROUND(
+            issue_gemm(tmem_base, op_kmajor(aDH4, 64), op_mnmajor(aW4, 64), 4, idesc_full(128, 64, 0, 1), false);
+            issue_gemm(tmem_base + kColDW4, op_mnmajor(aDH4, 64), op_mnmajor(aH3, 64), 8, idesc_full(64, 64, 1, 1), !first))
+        epilogue_relu_bwd(tmem_row, smem + kH3, smem + kH4, tid);      // dH3 -> H4's buffer (H4 is dead)
+        // R3: dX3 = dH3 W3 ;  dW3 += dH3^T X3
+        NGP_ROUND(
+            issue_gemm(tmem_base, op_kmajor(aH4, 64), op_mnmajor(aW3, 32), 4, idesc_full(128, 32, 0, 1), false);
+            issue_gemm(tmem_base + kColDW3, op_mnmajor(aH4, 64), op_mnmajor(aX3, 32), 8, idesc_full(64, 32, 1, 1), !first))
+        {
+            // dh = dX3[:, 16:32] (+ TruncExp backward on h[:,0], networks.py:26-30), fp16
+            float g[16];
+            tmem_ld16(tmem_row + 16, g);
+            const float ds = __half2float(__float2half_rn(dsig * expf(fminf(fmaxf(h0, -15.0f), 15.0f))));
+            g[0] = __half2float(__float2half_rn(g[0])) + ds;
+            *reinterpret_cast<uint4*>(smem + kDH + chunk_off(tid, 0, 16)) =
+                make_uint4(pack_h2(g[0], g[1]), pack_h2(g[2], g[3]), pack_h2(g[4], g[5]), pack_h2(g[6], g[7]));
+            *reinterpret_cast<uint4*>(smem + kDH + chunk_off(tid, 1, 16)) =
+                make_uint4(pack_h2(g[8], g[9]), pack_h2(g[10], g[11]), pack_h2(g[12], g[13]), pack_h2(g[14], g[15]));
+        }
+        // R4: dH1pre = dh W2 ;  dW2^T += H1^T dh
+        NGP_ROUND(
+            issue_gemm(tmem_base, op_kmajor(aDH, 16), op_mnmajor(aW2, 64), 1, idesc_full(128, 64, 0, 1), false);
+            issue_gemm(tmem_base + kColDW2T, op_mnmajor(aH1, 64), op_mnmajor(aDH, 16), 8, idesc_full(64, 16, 1, 1), !first))
+        epilogue_relu_bwd(tmem_row, smem + kH1, smem + kH3, tid);      // dH1 -> H3's buffer (H3 is dead)
+        // R5: dE = dH1 W1 ;  dW1 += dH1^T E
+        NGP_ROUND(
+            issue_gemm(tmem_base, op_kmajor(aH3, 64), op_mnmajor(aW1, 32), 4, idesc_full(128, 32, 0, 1), false);
+            issue_gemm(tmem_base + kColDW1, op_mnmajor(aH3, 64), op_mnmajor(aE, 32), 8, idesc_full(64, 32, 1, 1), !first))
+        {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                float v[16];
+                tmem_ld16(tmem_row + g * 16, v);
+                if (valid) {
+                    if constexpr (sizeof(TEmb) == 2) {
+                        uint4* o = reinterpret_cast<uint4*>(demb + i * 32 + g * 16);
+                        o[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                        o[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+                    } else {
+                        float4* o = reinterpret_cast<float4*>(demb + i * 32 + g * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {  // fp16-rounded like the autocast graph, stored as fp32
+                            o[q] = make_float4(__half2float(__float2half_rn(v[4 * q])), __half2float(__float2half_rn(v[4 * q + 1])),
+                                               __half2float(__float2half_rn(v[4 * q + 2])), __half2float(__float2half_rn(v[4 * q + 3])));
+                        }
+                    }
+                }
+            }
+        }
+        first = false;
+        tc_fence_before();
+        __syncthreads();
+    }
+#undef NGP_ROUND
+
+    // ---- flush the weight-gradient accumulators: M = 64 rows live on TMEM lanes (m%16) + 32*(m/16)
+    if (!first) {
+        const int m = warp * 16 + lane;  // row held by this thread when lane < 16
+        const bool has_row = lane < 16;
+        float v[16];
+        // dW4 [64 out x 64 in]
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            tmem_ld16(tmem_row + kColDW4 + g * 16, v);
+            if (has_row)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(grad_w + (NGP_MLP_W1 + NGP_MLP_W2 + NGP_MLP_W3) + m * 64 + g * 16 + j, v[j]);
+        }
+        // dW1 [64 out x 32 in], dW3 [64 out x 32 in]
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            tmem_ld16(tmem_row + kColDW1 + g * 16, v);
+            if (has_row)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(grad_w + m * 32 + g * 16 + j, v[j]);
+            tmem_ld16(tmem_row + kColDW3 + g * 16, v);
+            if (has_row)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(grad_w + (NGP_MLP_W1 + NGP_MLP_W2) + m * 32 + g * 16 + j, v[j]);
+        }
+        // dW2^T [64 in x 16 out] -> W2 is [16 out x 64 in]
+        tmem_ld16(tmem_row + kColDW2T, v);
+        if (has_row)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(grad_w + NGP_MLP_W1 + j * 64 + m, v[j]);
+        // dW5^T [64 in x 16 (3 used)] -> W5 is [3 out x 64 in]
+        tmem_ld16(tmem_row + kColDW5T, v);
+        if (has_row)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) atomicAdd(grad_w + (NGP_MLP_W1 + NGP_MLP_W2 + NGP_MLP_W3 + NGP_MLP_W4) + j * 64 + m, v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemColsBwd);
+}
+
+template <typename TEmb>
+int launch_bwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, const float* dsigmas, const void* drgbs,
+               void* demb, float* grad_w, int64_t n, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel<TEmb>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesBwd);
+        if (e != cudaSuccess) {
+            ngp::set_error("mlp_bwd_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    const int64_t max_ctas = (int64_t)ngp::sm_count() * 2;  // 108 KB smem + 256 TMEM columns per CTA
+    const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
+    mlp_bwd_kernel<TEmb><<<grid, kThreads, kSmemBytesBwd, st>>>((const TEmb*)emb, dirs, *w, dsigmas, (const __half*)drgbs,
+                                                               (TEmb*)demb, grad_w, n);
+    NGP_LAUNCHED("mlp_bwd_kernel");
+    return 0;
+}
+
 template <typename TEmb>
 int launch_fwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, float* sigmas, void* rgbs, int64_t n,
                cudaStream_t st) {
@@ -388,10 +711,21 @@ int ngp_mlp_fwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp
 
 int ngp_mlp_bwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
                 const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n, void* stream) {
-    (void)emb; (void)emb_dtype; (void)dirs; (void)w; (void)save; (void)dsigmas; (void)drgbs_f16; (void)demb;
-    (void)grad_w; (void)n; (void)stream;
-    ngp::set_error("ngp_mlp_bwd: not implemented yet");
-    return -2;
+    (void)save;
+    NGP_REQUIRE(n >= 0, "negative n");
+    NGP_REQUIRE(emb_dtype == NGP_F32 || emb_dtype == NGP_F16, "bad dtype");
+    if (n == 0) return 0;
+    NGP_REQUIRE(emb && dirs && w && dsigmas && drgbs_f16 && demb && grad_w, "null pointer");
+    NGP_REQUIRE(w->w1 && w->w2 && w->w3 && w->w4 && w->w5, "null weight pointer");
+    NGP_REQUIRE(((reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(demb)) & 15) == 0,
+                "emb/demb must be 16-byte aligned");
+    const uintptr_t wal = reinterpret_cast<uintptr_t>(w->w1) | reinterpret_cast<uintptr_t>(w->w2) |
+                          reinterpret_cast<uintptr_t>(w->w3) | reinterpret_cast<uintptr_t>(w->w4) |
+                          reinterpret_cast<uintptr_t>(w->w5);
+    NGP_REQUIRE((wal & 15) == 0, "weights must be 16-byte aligned");
+    cudaStream_t st = ngp::as_stream(stream);
+    if (emb_dtype == NGP_F16) return launch_bwd<__half>(emb, dirs, w, dsigmas, drgbs_f16, demb, grad_w, n, st);
+    return launch_bwd<float>(emb, dirs, w, dsigmas, drgbs_f16, demb, grad_w, n, st);
 }
 
 }  // extern "C"

@@ -359,3 +359,31 @@ def test_adam_fused(ops, oracle, n):
     assert int(found) == 1
     ops.adam_step(gp, g, gm, gv, 1e-2, 4, found_inf=found)
     assert np.array_equal(N(gp), before)
+
+
+@pytest.mark.parametrize("emb_half", [True, False])
+@pytest.mark.parametrize("n", [1, 128, 5000, 40000])
+def test_mlp_bwd_tcgen05_matches_oracle(ops, oracle, emb_half, n):
+    rng = np.random.default_rng(35)
+    emb = (rng.standard_normal((n, 32)) * 0.5).astype(np.float16 if emb_half else np.float32)
+    dirs = rng.standard_normal((n, 3)).astype(np.float32)
+    ws = _weights(rng)
+    dsig = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    drgb = (rng.standard_normal((n, 3)) * 0.1).astype(np.float16)
+    demb_ref, gw_ref = oracle.mlp_bwd(emb, dirs, ws, dsig, drgb)
+    demb, gw = ops.mlp_bwd(T(emb), T(dirs), [T(w) for w in ws], T(dsig), T(drgb))
+    demb, gw = N(demb).astype(np.float32), N(gw)
+    demb_ref = demb_ref.astype(np.float32)
+    # every intermediate gradient is rounded to fp16 on both sides; the tensor core sums K in a
+    # different order, so individual fp16 roundings can flip by 1 ulp (2^-11 relative): 5e-3 of the
+    # tensor's max magnitude bounds the propagated effect (north_star: 1e-3 relative on gradients
+    # is checked on the median below)
+    assert np.abs(demb - demb_ref).max() <= 5e-3 * np.abs(demb_ref).max()
+    assert np.abs(gw - gw_ref).max() <= 5e-3 * np.abs(gw_ref).max()
+    big = np.abs(gw_ref) > 0.05 * np.abs(gw_ref).max()
+    assert np.median(np.abs(gw[big] - gw_ref[big]) / np.abs(gw_ref[big])) < 1e-3
+    # per-layer blocks must all be populated (catches a transposed / misplaced dW block)
+    offs = np.cumsum([0, 2048, 1024, 2048, 4096, 192])
+    for a, b in zip(offs[:-1], offs[1:]):
+        blk, ref = gw[a:b], gw_ref[a:b]
+        assert np.abs(blk - ref).max() <= 5e-3 * max(np.abs(ref).max(), 1e-6), (a, b)
