@@ -113,6 +113,9 @@ class NGP(nn.Module):
         """x: (N, 3) in [-scale, scale] -> sigmas (N) [, h (N, 16)]  (networks.py:136-150)."""
         x = (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
         embedding = self.pos_encoder(x)
+        if not return_feat and not torch.is_grad_enabled() and self._fusable(x):
+            from taichi_nerfs_b200.fused_mlp import ngp_density
+            return ngp_density(self, embedding)
         h = self.xyz_encoder(embedding)
         sigmas = TruncExp.apply(h[:, 0])
         if return_feat:
