@@ -148,29 +148,167 @@ __global__ void __launch_bounds__(256) ray_aabb_kernel(const float* __restrict__
     reinterpret_cast<float2*>(hits_t)[r] = out;
 }
 
-// ---- a2 pass 1 -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) march_count_kernel(const float* __restrict__ rays_o,
-                                                          const float* __restrict__ rays_d,
-                                                          const float* __restrict__ hits_t,
-                                                          const float* __restrict__ noise, MarchParams p,
-                                                          int max_samples, int32_t* __restrict__ rays_a,
-                                                          int64_t n) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// ---- a2: warp-per-ray marching ---------------------------------------------------------------------
+// The reference walks each ray with one thread (ray_march.py:27, block_dim=128): ~530 dependent grid
+// steps per Lego ray, with divergent inner while-loops.  The sequence of candidate positions
+// t_0, t_{k+1} = t_k + calc_dt(t_k) does NOT depend on occupancy (both the occupied branch and the
+// skip loop advance by calc_dt(t)), so a warp can take one ray: every lane recomputes the same
+// 32-step t chain (cheap, keeps it bit-identical to the sequential fp32 recurrence), lane k tests
+// position k against the bitfield, and the "which positions are actually visited" logic (emit if
+// occupied, else jump to the first position >= the cell's exit time) is resolved with ballots and a
+// short shuffle pointer walk.  Samples come out in the same order with the same bits.
+struct CellTest {
+    float xyz[3];
+    float dt;
+    float t_target;  // exit time of the (empty) cell, ray_march.py:66-71
+    bool occ;
+};
+
+__device__ __forceinline__ CellTest test_cell(const MarchParams& p, const Ray& ray, float tt, float dt) {
+    CellTest c;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c.xyz[k] = f_add(ray.o[k], f_mul(tt, ray.d[k]));
+    c.dt = dt;
+    int mip = 0;
+    if (p.cascades > 1) {
+        const float mx = fmaxf(fmaxf(fabsf(c.xyz[0]), fabsf(c.xyz[1])), fabsf(c.xyz[2]));
+        const int m_pos = min(p.cascades - 1, max(0, frexp_bit(mx) + 1));
+        const int m_dt = min(p.cascades - 1, max(0, frexp_bit(f_mul(dt, p.gsf))));
+        mip = max(m_pos, m_dt);
+    }
+    const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + mip - 1) << 23), p.scale);
+    const float mip_bound_inv = f_div(1.0f, mip_bound);
+    float nxyz[3];
+    uint32_t u[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = f_mul(f_mul(0.5f, f_add(f_mul(c.xyz[k], mip_bound_inv), 1.0f)), p.gsf);
+        v = fminf(fmaxf(v, 0.0f), f_sub(p.gsf, 1.0f));
+        nxyz[k] = v;
+        u[k] = __float2uint_rz(v);
+    }
+    const uint32_t idx = (uint32_t)mip * p.gs3 + morton3d(u[0], u[1], u[2]);
+    c.occ = ((uint32_t)__ldg(p.bits + (idx >> 3)) & (1u << (idx & 7u))) != 0;
+    float tmin = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float a = f_add(f_add(nxyz[k], 0.5f), f_mul(0.5f, fsign(ray.d[k])));
+        a = f_sub(f_mul(f_mul(a, p.gs_inv), 2.0f), 1.0f);
+        a = f_mul(f_sub(f_mul(a, mip_bound), c.xyz[k]), ray.dinv[k]);
+        tmin = fminf(tmin, a);
+    }
+    c.t_target = f_add(tt, fmaxf(0.0f, tmin));
+    return c;
+}
+
+constexpr int kRaysPerBlock = 4;
+
+template <bool kWrite>
+__global__ void __launch_bounds__(kRaysPerBlock * 32)
+march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                        const float* __restrict__ hits_t, const float* __restrict__ noise, MarchParams p,
+                        int max_samples, int32_t* __restrict__ rays_a, int32_t* __restrict__ counter,
+                        float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                        float* __restrict__ ts, int64_t n, int64_t capacity) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
     if (r >= n) return;
+    const unsigned full = 0xffffffffu;
+
+    int limit = max_samples;
+    int64_t start = 0;
+    if (kWrite) {
+        start = rays_a[r * 3 + 1];
+        limit = rays_a[r * 3 + 2];
+        if (start + limit > capacity) {  // does not fit: drop the ray's samples (dropped rays form a suffix)
+            if (lane == 0) {
+                rays_a[r * 3 + 2] = 0;
+                atomicMin(&counter[0], (int32_t)start);
+            }
+            return;
+        }
+        if (limit == 0) return;
+    }
     Ray ray;
     load_ray(rays_o, rays_d, r, ray);
     const float t2 = hits_t[r * 2 + 1];
     float t = train_t0(hits_t, noise, r, p);
-    int cnt = 0;
-    float xyz[3], dt;
-    while (0.0f <= t && t < t2 && cnt < max_samples) {  // ray_march.py:43
-        if (march_step(p, ray, t, xyz, dt)) {
-            t = f_add(t, dt);
-            cnt += 1;
+    int emitted = 0;
+    float skip_until = -INFINITY;
+    const bool const_dt = p.esf == 0.0f;
+    const float dt0 = calc_dt(t, p.esf, p.dt_max);
+
+    while (0.0f <= t && t < t2 && emitted < limit) {  // ray_march.py:43 / :86 (warp-uniform)
+        // t chain: position k of this chunk, identical on every lane
+        float tk = t, my_t = t, my_dt = dt0;
+        if (const_dt) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (k == lane) my_t = tk;
+                tk = f_add(tk, dt0);
+            }
+        } else {
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const float dk = calc_dt(tk, p.esf, p.dt_max);
+                if (k == lane) {
+                    my_t = tk;
+                    my_dt = dk;
+                }
+                tk = f_add(tk, dk);
+            }
         }
+        const bool valid = my_t < t2;
+        const CellTest c = test_cell(p, ray, my_t, my_dt);
+        const unsigned valid_mask = __ballot_sync(full, valid);
+        const unsigned occ_mask = __ballot_sync(full, valid && c.occ);
+
+        // empty lanes: first position j > lane with t_j >= t_target (at least one step, ray_march.py:72-74)
+        int lo = lane + 1, hi = 32;
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const int mid = (lo + hi) >> 1;
+            const float tm = __shfl_sync(full, my_t, min(mid, 31));
+            if (lo < hi) {
+                if (tm < c.t_target) lo = mid + 1;
+                else hi = mid;
+            }
+        }
+        const int nxt = lo;
+
+        // positions still inside the cell skipped at the end of the previous chunk
+        int pos = __popc(__ballot_sync(full, my_t < skip_until));
+        skip_until = -INFINITY;
+        unsigned emit = 0;
+        while (pos < 32 && ((valid_mask >> pos) & 1u) && emitted + __popc(emit) < limit) {
+            if ((occ_mask >> pos) & 1u) {
+                emit |= 1u << pos;
+                pos += 1;
+            } else {
+                const int q = pos;
+                pos = __shfl_sync(full, nxt, q);
+                if (pos >= 32) skip_until = __shfl_sync(full, c.t_target, q);
+            }
+        }
+        if (kWrite && ((emit >> lane) & 1u)) {
+            const int64_t i = start + emitted + __popc(emit & ((1u << lane) - 1u));
+            xyzs[i * 3 + 0] = c.xyz[0];
+            xyzs[i * 3 + 1] = c.xyz[1];
+            xyzs[i * 3 + 2] = c.xyz[2];
+            dirs[i * 3 + 0] = ray.d[0];
+            dirs[i * 3 + 1] = ray.d[1];
+            dirs[i * 3 + 2] = ray.d[2];
+            ts[i] = my_t;
+            deltas[i] = c.dt;
+        }
+        emitted += __popc(emit);
+        if (valid_mask != full) break;  // the ray left the box inside this chunk
+        t = tk;
     }
-    rays_a[r * 3 + 0] = (int32_t)r;
-    rays_a[r * 3 + 2] = cnt;
+    if (!kWrite && lane == 0) {
+        rays_a[r * 3 + 0] = (int32_t)r;
+        rays_a[r * 3 + 2] = emitted;
+    }
 }
 
 // exclusive scan of rays_a[:,2] into rays_a[:,1] by one CTA; counter = (total, n_rays)
@@ -212,49 +350,6 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(int32_t* __restrict__ 
     if (tid == 0) {
         counter[0] = carry_s;
         counter[1] = (int32_t)n;
-    }
-}
-
-// ---- a2 pass 2 -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) march_write_kernel(const float* __restrict__ rays_o,
-                                                          const float* __restrict__ rays_d,
-                                                          const float* __restrict__ hits_t,
-                                                          const float* __restrict__ noise, MarchParams p,
-                                                          int32_t* __restrict__ rays_a,
-                                                          int32_t* __restrict__ counter,
-                                                          float* __restrict__ xyzs, float* __restrict__ dirs,
-                                                          float* __restrict__ deltas, float* __restrict__ ts,
-                                                          int64_t n, int64_t capacity) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const int64_t start = rays_a[r * 3 + 1];
-    const int cnt = rays_a[r * 3 + 2];
-    if (start + cnt > capacity) {  // does not fit: drop the ray's samples, flag via counter[1] < 0
-        rays_a[r * 3 + 2] = 0;
-        atomicMin(&counter[0], (int32_t)start);  // dropped rays form a suffix: total = first dropped start
-        return;
-    }
-    if (cnt == 0) return;
-    Ray ray;
-    load_ray(rays_o, rays_d, r, ray);
-    const float t2 = hits_t[r * 2 + 1];
-    float t = train_t0(hits_t, noise, r, p);
-    int s = 0;
-    float xyz[3], dt;
-    while (t < t2 && s < cnt) {  // ray_march.py:86
-        if (march_step(p, ray, t, xyz, dt)) {
-            const int64_t i = start + s;
-            xyzs[i * 3 + 0] = xyz[0];
-            xyzs[i * 3 + 1] = xyz[1];
-            xyzs[i * 3 + 2] = xyz[2];
-            dirs[i * 3 + 0] = ray.d[0];
-            dirs[i * 3 + 1] = ray.d[1];
-            dirs[i * 3 + 2] = ray.d[2];
-            ts[i] = t;
-            deltas[i] = dt;
-            t = f_add(t, dt);
-            s += 1;
-        }
     }
 }
 
@@ -337,10 +432,11 @@ int ngp_raymarching_train_count(const float* rays_o, const float* rays_d, const 
     cudaStream_t st = ngp::as_stream(stream);
     const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
     if (n_rays > 0) {
-        const int block = 128;
-        march_count_kernel<<<(unsigned)((n_rays + block - 1) / block), block, 0, st>>>(
-            rays_o, rays_d, hits_t, noise, p, max_samples, rays_a, n_rays);
-        NGP_LAUNCHED("march_count_kernel");
+        const unsigned grid = (unsigned)((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
+        march_train_warp_kernel<false><<<grid, kRaysPerBlock * 32, 0, st>>>(
+            rays_o, rays_d, hits_t, noise, p, max_samples, rays_a, counter, nullptr, nullptr, nullptr, nullptr,
+            n_rays, 0);
+        NGP_LAUNCHED("march_train_warp_kernel<count>");
     }
     march_scan_kernel<<<1, 1024, 0, st>>>(rays_a, counter, n_rays);
     NGP_LAUNCHED("march_scan_kernel");
@@ -357,10 +453,10 @@ int ngp_raymarching_train_write(const float* rays_o, const float* rays_d, const 
     NGP_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && noise && rays_a && counter, "null pointer");
     NGP_REQUIRE(capacity == 0 || (xyzs && dirs && deltas && ts), "null output");
     const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
-    const int block = 128;
-    march_write_kernel<<<(unsigned)((n_rays + block - 1) / block), block, 0, ngp::as_stream(stream)>>>(
-        rays_o, rays_d, hits_t, noise, p, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity);
-    NGP_LAUNCHED("march_write_kernel");
+    const unsigned grid = (unsigned)((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
+    march_train_warp_kernel<true><<<grid, kRaysPerBlock * 32, 0, ngp::as_stream(stream)>>>(
+        rays_o, rays_d, hits_t, noise, p, 0, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity);
+    NGP_LAUNCHED("march_train_warp_kernel<write>");
     return 0;
 }
 
