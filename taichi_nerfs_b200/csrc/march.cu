@@ -276,18 +276,35 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
         }
         const int nxt = lo;
 
-        // positions still inside the cell skipped at the end of the previous chunk
-        int pos = __popc(__ballot_sync(full, my_t < skip_until));
-        skip_until = -INFINITY;
+        // Which positions does the sequential loop actually visit?  successor(j) = j+1 if occupied, else the
+        // jump target; positions at/after the box exit end the walk.  The orbit of the chunk's entry
+        // position under `successor` is found by pointer doubling (5 shuffle rounds) instead of a serial walk.
+        int F = valid ? (c.occ ? lane + 1 : nxt) : 32;
+        unsigned M = 1u << lane;
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const int src = min(F, 31);
+            const unsigned Mo = __shfl_sync(full, M, src);
+            const int Fo = __shfl_sync(full, F, src);
+            if (F < 32) {
+                M |= Mo;
+                F = Fo;
+            }
+        }
+        // entry position: skip the positions still inside the cell left at the end of the previous chunk
+        const int pos0 = __popc(__ballot_sync(full, my_t < skip_until));
         unsigned emit = 0;
-        while (pos < 32 && ((valid_mask >> pos) & 1u) && emitted + __popc(emit) < limit) {
-            if ((occ_mask >> pos) & 1u) {
-                emit |= 1u << pos;
-                pos += 1;
-            } else {
-                const int q = pos;
-                pos = __shfl_sync(full, nxt, q);
-                if (pos >= 32) skip_until = __shfl_sync(full, c.t_target, q);
+        if (pos0 < 32) {
+            const unsigned visited = __shfl_sync(full, M, pos0) & valid_mask;
+            emit = visited & occ_mask;
+            const int room = limit - emitted;
+            if (__popc(emit) > room) emit &= (1u << __fns(emit, 0, room + 1)) - 1u;  // max_samples cap
+            skip_until = -INFINITY;
+            if (visited) {
+                const int q = 31 - __clz(visited);  // last visited position
+                const int nq = __shfl_sync(full, nxt, q);
+                const float tq = __shfl_sync(full, c.t_target, q);
+                if (!((occ_mask >> q) & 1u) && nq >= 32) skip_until = tq;  // cell extends into the next chunk
             }
         }
         if (kWrite && ((emit >> lane) & 1u)) {
