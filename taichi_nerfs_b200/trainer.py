@@ -17,7 +17,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, parallel
 
 
 class NGPTrainer:
@@ -75,12 +75,11 @@ class NGPTrainer:
 
     def optimizer_step(self):
         self.step_count += 1
-        if self.world_size > 1:
-            torch.distributed.all_reduce(self.flat_grad, group=self.pg)
+        parallel.allreduce_gradients(self.flat_grad, self.pg)
         self.found_inf.zero_()
-        ops.check_finite(self.flat_grad, self.found_inf)
+        ops.check_finite(self.flat_grad, self.found_inf)  # after the sum: identical on every rank
         lr = self.lr_at(self.step_count - 1)
-        inv = 1.0 / (self.loss_scale * self.world_size)
+        inv = parallel.inv_grad_scale(self.loss_scale, self.world_size)
         enc = self.model.pos_encoder
         for p, (off, s) in zip(self.params, self.slices):
             shadow = self._shadow if (self._shadow is not None and p is enc.hash_table) else None
