@@ -29,10 +29,49 @@ def hemisphere_poses(n_poses: int, radius: float = 1.4, seed: int = 23) -> torch
     return torch.stack([right, down, front, pos], dim=-1).float()
 
 
+def analytic_scene(x):
+    """Closed-form teacher radiance field inside [-0.5,0.5]^3: three soft blobs and a box frame.
+    x: (..., 3) -> (sigma (...), rgb (..., 3))."""
+    centers = x.new_tensor([[0.15, 0.0, -0.1], [-0.2, 0.15, 0.05], [0.0, -0.2, 0.2]])
+    radii = x.new_tensor([0.18, 0.14, 0.10])
+    colors = x.new_tensor([[0.9, 0.75, 0.1], [0.1, 0.5, 0.9], [0.85, 0.2, 0.2]])
+    d2 = ((x[..., None, :] - centers) ** 2).sum(-1)                       # (..., 3)
+    dens = 60.0 * torch.sigmoid((radii ** 2 - d2) * 400.0)                 # soft spheres
+    sigma = dens.sum(-1)
+    rgb = (dens[..., None] * colors).sum(-2) / (sigma[..., None] + 1e-6)
+    return sigma, rgb.clamp(0, 1)
+
+
+@torch.no_grad()
+def render_teacher(rays_o, rays_d, n_samples: int = 192, scale: float = 0.5):
+    """Quadrature volume rendering of `analytic_scene` on a white background (synthetic-scene convention)."""
+    inv = 1.0 / rays_d
+    t0 = ((-scale - rays_o) * inv)
+    t1 = ((scale - rays_o) * inv)
+    near = torch.minimum(t0, t1).amax(-1).clamp_min(0.01)
+    far = torch.maximum(t0, t1).amin(-1)
+    hit = far > near
+    u = (torch.arange(n_samples, device=rays_o.device) + 0.5) / n_samples
+    t = near[:, None] + (far - near).clamp_min(0)[:, None] * u
+    dt = ((far - near).clamp_min(0) / n_samples)[:, None]
+    x = rays_o[:, None, :] + t[..., None] * rays_d[:, None, :]
+    sigma, rgb = analytic_scene(x)
+    alpha = 1 - torch.exp(-sigma * dt)
+    T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1 - alpha + 1e-10], 1), 1)[:, :-1]
+    w = alpha * T * hit[:, None]
+    out = (w[..., None] * rgb).sum(1) + (1 - w.sum(1))[:, None]
+    return out
+
+
 class SyntheticLego:
     def __init__(self, n_images: int = 100, img_wh=(800, 800), focal: float = 1111.111, radius: float = 1.4,
-                 split: str = 'train', batch_size: int = 8192, seed: int = 23, with_rgb: bool = True):
-        w, h = img_wh
+                 split: str = 'train', batch_size: int = 8192, seed: int = 23, with_rgb: bool = True,
+                 scene: str = 'random', root_dir: str = '', downsample: float = 1.0, **_):
+        w, h = int(img_wh[0] * downsample), int(img_wh[1] * downsample)
+        focal = focal * downsample
+        if split != 'train' and not split.startswith('train'):
+            seed = seed + 1000  # held-out poses
+        self.scene = scene
         self.img_wh = (w, h)
         self.split = split
         self.batch_size = batch_size
@@ -63,6 +102,17 @@ class SyntheticLego:
             pix = torch.randint(0, self.img_wh[0] * self.img_wh[1], (n,), device=dev, generator=self._gen)
             sample = {'img_idxs': img, 'pix_idxs': pix, 'pose': self.poses[img], 'direction': self.directions[pix]}
             if self.with_rgb:
-                sample['rgb'] = torch.rand(n, 3, device=dev, generator=self._gen)
+                if self.scene == 'analytic':
+                    from .ray_utils import get_rays
+                    o, d = get_rays(sample['direction'], sample['pose'])
+                    sample['rgb'] = render_teacher(o, d)
+                else:
+                    sample['rgb'] = torch.rand(n, 3, device=dev, generator=self._gen)
             return sample
-        return {'pose': self.poses[idx], 'img_idxs': idx}
+        sample = {'pose': self.poses[idx], 'img_idxs': idx}
+        if self.scene == 'analytic':
+            from .ray_utils import get_rays
+            o, d = get_rays(self.directions, self.poses[idx])
+            sample['rgb'] = torch.cat([render_teacher(o[i:i + 65536], d[i:i + 65536])
+                                       for i in range(0, o.shape[0], 65536)])
+        return sample

@@ -183,6 +183,17 @@ int ngp_composite_test(const float* sigmas, const void* rgbs, int rgbs_dtype,
                        float* opacity, float* depth, float* rgb,
                        int64_t n_alive, void* stream);
 
+/* ---- distortion loss -------------------------------------- */
+/* replaces prefix_sums_kernel + _loss_kernel + distortion_loss_fw_kernel
+ * (modules/distortion.py:15-84): loss[ray] = sum_s 2*(wts_inc*ws_exc - ws_inc*wts_exc) + w^2*delta/3
+ * with per-ray inclusive/exclusive scans of w and w*t. */
+int ngp_distortion_fwd(const float* ws, const float* deltas, const float* ts, const int32_t* rays_a,
+                       float* loss, int64_t n_rays, int64_t n_samples, void* stream);
+/* replaces distortion_loss_bw_kernel (modules/distortion.py:86-119) */
+int ngp_distortion_bwd(const float* dL_dloss, const float* ws, const float* deltas, const float* ts,
+                       const int32_t* rays_a, float* dL_dws, int64_t n_rays, int64_t n_samples,
+                       void* stream);
+
 /* ---- occupancy-grid helpers ---------------------------- */
 /* replaces packbits, modules/utils.py:157-169 */
 int ngp_packbits(const float* density_grid, float density_threshold,

@@ -829,6 +829,56 @@ int ngp_composite_test_cpu(const float* sigmas, const void* rgbs, int rgbs_dtype
 }
 
 /* ------------------------------------------------------------------------- */
+/* distortion loss                     modules/distortion.py:15-119           */
+/* ------------------------------------------------------------------------- */
+int ngp_distortion_fwd_cpu(const float* ws, const float* deltas, const float* ts, const int32_t* rays_a,
+                           float* loss, int64_t n_rays, int64_t n_samples) {
+    (void)n_samples;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n_rays; ++i) {
+        const int64_t ray = rays_a[i * 3 + 0], start = rays_a[i * 3 + 1];
+        const int N = rays_a[i * 3 + 2];
+        float ws_t = 0.f, wts_t = 0.f, acc = 0.f;
+        for (int n = 0; n < N; ++n) { /* prefix_sums_kernel :28-44 fused with _loss_kernel :55-64 */
+            const int64_t s = start + n;
+            const float ws_exc = ws_t, wts_exc = wts_t;
+            ws_t += ws[s];
+            wts_t += ws[s] * ts[s];
+            acc += 2.f * (wts_t * ws_exc - ws_t * wts_exc) + 1.f / 3.f * ws[s] * ws[s] * deltas[s];
+        }
+        loss[ray] = acc; /* :82 */
+    }
+    return 0;
+}
+
+int ngp_distortion_bwd_cpu(const float* dL_dloss, const float* ws, const float* deltas, const float* ts,
+                           const int32_t* rays_a, float* dL_dws, int64_t n_rays, int64_t n_samples) {
+    (void)n_samples;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n_rays; ++i) {
+        const int64_t ray = rays_a[i * 3 + 0], start = rays_a[i * 3 + 1];
+        const int N = rays_a[i * 3 + 2];
+        float ws_sum = 0.f, wts_sum = 0.f;
+        for (int n = 0; n < N; ++n) {
+            ws_sum += ws[start + n];
+            wts_sum += ws[start + n] * ts[start + n];
+        }
+        float ws_inc = 0.f, wts_inc = 0.f;
+        const float g = dL_dloss[ray];
+        for (int n = 0; n < N; ++n) { /* :104-117 */
+            const int64_t s = start + n;
+            const float selector = n == 0 ? 0.f : ts[s] * ws_inc - wts_inc; /* scans up to s-1 */
+            ws_inc += ws[s];
+            wts_inc += ws[s] * ts[s];
+            float d = g * 2.f * (selector + (wts_sum - wts_inc - ts[s] * (ws_sum - ws_inc)));
+            d += g * 2.f / 3.f * ws[s] * deltas[s];
+            dL_dws[s] = d;
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* occupancy-grid helpers              modules/utils.py:120-169               */
 /* ------------------------------------------------------------------------- */
 int ngp_packbits_cpu(const float* density_grid, float density_threshold, uint8_t* density_bitfield,

@@ -240,6 +240,24 @@ def composite_test(sigmas, rgbs, deltas, ts, pack_info, alive_indices, T_thresho
                                       _p(rgb), C.c_int64(alive_indices.shape[0])))
 
 
+def distortion_fwd(ws, deltas, ts, rays_a):
+    w, dl, t = _c(ws, np.float32), _c(deltas, np.float32), _c(ts, np.float32)
+    ra = _c(rays_a, np.int32)
+    loss = np.zeros(ra.shape[0], np.float32)
+    _chk(lib().ngp_distortion_fwd_cpu(_p(w), _p(dl), _p(t), _p(ra), _p(loss), C.c_int64(ra.shape[0]),
+                                      C.c_int64(w.shape[0])))
+    return loss
+
+
+def distortion_bwd(dL_dloss, ws, deltas, ts, rays_a):
+    g, w, dl, t = _c(dL_dloss, np.float32), _c(ws, np.float32), _c(deltas, np.float32), _c(ts, np.float32)
+    ra = _c(rays_a, np.int32)
+    out = np.zeros(w.shape[0], np.float32)
+    _chk(lib().ngp_distortion_bwd_cpu(_p(g), _p(w), _p(dl), _p(t), _p(ra), _p(out), C.c_int64(ra.shape[0]),
+                                      C.c_int64(w.shape[0])))
+    return out
+
+
 def packbits(density_grid, threshold):
     g = _c(density_grid, np.float32).reshape(-1)
     out = np.empty(g.shape[0] // 8, np.uint8)

@@ -265,9 +265,99 @@ composite_test_kernel(const float* __restrict__ sigmas, const TRgb* __restrict__
     opacity[ray] += op;
 }
 
+// ---- distortion loss (Mip-NeRF 360), modules/distortion.py:15-119 -----------------------------------
+// warp per ray; per-ray scans of w and w*t are warp prefix sums carried across 32-sample chunks
+// (the reference's TODO at distortion.py:4-6 asks for exactly this shared/warp scan).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+distortion_fwd_kernel(const float* __restrict__ ws, const float* __restrict__ deltas, const float* __restrict__ ts,
+                      const int32_t* __restrict__ rays_a, float* __restrict__ loss, int64_t n_rays) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (i >= n_rays) return;
+    const int64_t ray = rays_a[i * 3 + 0], start = rays_a[i * 3 + 1];
+    const int N = rays_a[i * 3 + 2];
+    float cw = 0.f, cwt = 0.f, acc = 0.f;  // carries = scans up to the previous chunk
+    for (int base = 0; base < N; base += 32) {
+        const int k = base + lane;
+        const bool valid = k < N;
+        const float w = valid ? ws[start + k] : 0.f;
+        const float t = valid ? ts[start + k] : 0.f;
+        const float d = valid ? deltas[start + k] : 0.f;
+        const float wt = w * t;
+        const float w_inc = cw + warp_scan_add(w, lane), wt_inc = cwt + warp_scan_add(wt, lane);
+        const float w_exc = w_inc - w, wt_exc = wt_inc - wt;
+        if (valid) acc += 2.f * (wt_inc * w_exc - w_inc * wt_exc) + (1.f / 3.f) * w * w * d;
+        cw = __shfl_sync(0xffffffffu, w_inc, 31);
+        cwt = __shfl_sync(0xffffffffu, wt_inc, 31);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) loss[ray] = acc;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+distortion_bwd_kernel(const float* __restrict__ dL_dloss, const float* __restrict__ ws,
+                      const float* __restrict__ deltas, const float* __restrict__ ts,
+                      const int32_t* __restrict__ rays_a, float* __restrict__ dL_dws, int64_t n_rays) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (i >= n_rays) return;
+    const int64_t ray = rays_a[i * 3 + 0], start = rays_a[i * 3 + 1];
+    const int N = rays_a[i * 3 + 2];
+    float w_sum = 0.f, wt_sum = 0.f;
+    for (int k = lane; k < N; k += 32) {
+        const float w = ws[start + k];
+        w_sum += w;
+        wt_sum += w * ts[start + k];
+    }
+    w_sum = warp_sum(w_sum);
+    wt_sum = warp_sum(wt_sum);
+    const float g = dL_dloss[ray];
+    float cw = 0.f, cwt = 0.f;
+    for (int base = 0; base < N; base += 32) {
+        const int k = base + lane;
+        const bool valid = k < N;
+        const float w = valid ? ws[start + k] : 0.f;
+        const float t = valid ? ts[start + k] : 0.f;
+        const float wt = w * t;
+        const float w_inc = cw + warp_scan_add(w, lane), wt_inc = cwt + warp_scan_add(wt, lane);
+        const float w_exc = w_inc - w, wt_exc = wt_inc - wt;
+        if (valid) {
+            const float selector = k == 0 ? 0.f : t * w_exc - wt_exc;  // distortion.py:110
+            float d = g * 2.f * (selector + (wt_sum - wt_inc - t * (w_sum - w_inc)));
+            d += g * (2.f / 3.f) * w * deltas[start + k];
+            dL_dws[start + k] = d;
+        }
+        cw = __shfl_sync(0xffffffffu, w_inc, 31);
+        cwt = __shfl_sync(0xffffffffu, wt_inc, 31);
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int ngp_distortion_fwd(const float* ws, const float* deltas, const float* ts, const int32_t* rays_a, float* loss,
+                       int64_t n_rays, int64_t n_samples, void* stream) {
+    NGP_REQUIRE(n_rays >= 0 && n_samples >= 0, "negative size");
+    if (n_rays == 0) return 0;
+    NGP_REQUIRE(rays_a && loss && (n_samples == 0 || (ws && deltas && ts)), "null pointer");
+    const unsigned grid = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    distortion_fwd_kernel<<<grid, kWarpsPerBlock * 32, 0, ngp::as_stream(stream)>>>(ws, deltas, ts, rays_a, loss, n_rays);
+    NGP_LAUNCHED("distortion_fwd_kernel");
+    return 0;
+}
+
+int ngp_distortion_bwd(const float* dL_dloss, const float* ws, const float* deltas, const float* ts,
+                       const int32_t* rays_a, float* dL_dws, int64_t n_rays, int64_t n_samples, void* stream) {
+    NGP_REQUIRE(n_rays >= 0 && n_samples >= 0, "negative size");
+    if (n_rays == 0 || n_samples == 0) return 0;
+    NGP_REQUIRE(dL_dloss && ws && deltas && ts && rays_a && dL_dws, "null pointer");
+    const unsigned grid = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    distortion_bwd_kernel<<<grid, kWarpsPerBlock * 32, 0, ngp::as_stream(stream)>>>(dL_dloss, ws, deltas, ts, rays_a,
+                                                                                     dL_dws, n_rays);
+    NGP_LAUNCHED("distortion_bwd_kernel");
+    return 0;
+}
 
 int ngp_dir_encode(const float* dirs, float* out, int64_t n, void* stream) {
     NGP_REQUIRE(n >= 0, "negative n");

@@ -163,6 +163,22 @@ def composite_test(sigmas, rgbs, deltas, ts, pack_info, alive_indices, T_thresho
           "composite_test")
 
 
+# ---- distortion loss ---------------------------------------------------------------------------------
+def distortion_fwd(ws, deltas, ts, rays_a):
+    _need_cuda(ws, deltas, ts, rays_a)
+    loss = torch.zeros(rays_a.shape[0], device=ws.device, dtype=torch.float32)
+    check(load().ngp_distortion_fwd(_ptr(ws), _ptr(deltas), _ptr(ts), _ptr(rays_a), _ptr(loss), rays_a.shape[0],
+                                    ws.shape[0], _stream()), "distortion_fwd")
+    return loss
+
+
+def distortion_bwd(dL_dloss, ws, deltas, ts, rays_a):
+    out = torch.zeros_like(ws)
+    check(load().ngp_distortion_bwd(_ptr(dL_dloss), _ptr(ws), _ptr(deltas), _ptr(ts), _ptr(rays_a), _ptr(out),
+                                    rays_a.shape[0], ws.shape[0], _stream()), "distortion_bwd")
+    return out
+
+
 # ---- occupancy grid helpers ------------------------------------------------------------------------
 def packbits(density_grid, threshold, bitfield):
     _need_cuda(density_grid, bitfield)

@@ -65,11 +65,13 @@ class NGPTrainer:
         eta_min = self.lr0 / 30
         return eta_min + (self.lr0 - eta_min) * (1 + math.cos(math.pi * min(step, self.max_steps) / self.max_steps)) / 2
 
-    def forward_backward(self, rays_o, rays_d, rgb_gt, exp_step_factor=0.0):
+    def forward_backward(self, rays_o, rays_d, rgb_gt, exp_step_factor=0.0, extra_loss=None):
         from modules.rendering import render
         with torch.autocast(device_type='cuda', dtype=torch.float16):
             results = render(self.model, rays_o, rays_d, exp_step_factor=exp_step_factor)
             loss = F.mse_loss(results['rgb'], rgb_gt)
+            if extra_loss is not None:  # e.g. distortion loss (train.py:194-195)
+                loss = loss + extra_loss(results)
         (loss * self.loss_scale).backward()
         return loss, results
 
@@ -89,7 +91,7 @@ class NGPTrainer:
             if shadow is not None:
                 enc.adopt_shadow(shadow)
 
-    def step(self, rays_o, rays_d, rgb_gt, exp_step_factor=0.0):
-        loss, results = self.forward_backward(rays_o, rays_d, rgb_gt, exp_step_factor)
+    def step(self, rays_o, rays_d, rgb_gt, exp_step_factor=0.0, extra_loss=None):
+        loss, results = self.forward_backward(rays_o, rays_d, rgb_gt, exp_step_factor, extra_loss)
         self.optimizer_step()
         return loss, results

@@ -387,3 +387,22 @@ def test_mlp_bwd_tcgen05_matches_oracle(ops, oracle, emb_half, n):
     for a, b in zip(offs[:-1], offs[1:]):
         blk, ref = gw[a:b], gw_ref[a:b]
         assert np.abs(blk - ref).max() <= 5e-3 * max(np.abs(ref).max(), 1e-6), (a, b)
+
+
+def test_distortion_loss(ops, oracle):
+    rng = np.random.default_rng(36)
+    rays_a, sig, rgbs, deltas, ts = _composite_inputs(rng, 600, 200, False, False)
+    S = sig.shape[0]
+    ws = (rng.random(S) * 0.05).astype(np.float32)
+    ref = oracle.distortion_fwd(ws, deltas, ts, rays_a)
+    got = N(ops.distortion_fwd(T(ws), T(deltas), T(ts), T(rays_a)))
+    np.testing.assert_allclose(got, ref, rtol=1e-3, atol=1e-6)  # warp scans vs sequential sums
+    g = rng.standard_normal(rays_a.shape[0]).astype(np.float32)
+    dref = oracle.distortion_bwd(g, ws, deltas, ts, rays_a)
+    dgot = N(ops.distortion_bwd(T(g), T(ws), T(deltas), T(ts), T(rays_a)))
+    assert np.abs(dgot - dref).max() <= 1e-3 * np.abs(dref).max()
+    from modules.distortion import distortion_loss
+    w = T(ws).requires_grad_(True)
+    distortion_loss({'ws': w, 'deltas': T(deltas), 'ts': T(ts), 'rays_a': T(rays_a)}).mean().backward()
+    assert np.abs(N(w.grad) - oracle.distortion_bwd(np.full(rays_a.shape[0], 1 / rays_a.shape[0], np.float32),
+                                                    ws, deltas, ts, rays_a)).max() <= 1e-3 * np.abs(N(w.grad)).max()

@@ -431,3 +431,33 @@ def test_adam_matches_torch(oracle):
     assert oracle.check_finite(g) == 1
     oracle.adam_step(p, g, m, v, 1e-2, 6, found_inf=1)
     assert np.array_equal(p, before)
+
+
+def test_distortion_matches_numpy_and_fd(oracle):
+    rng = np.random.default_rng(17)
+    rays_a, sig, rgbs, deltas, ts = _composite_inputs(rng, n_rays=20, max_n=30)
+    S = sig.shape[0]
+    ws = rng.random(S).astype(np.float32) * 0.1
+    # O(n^2) definition of the Mip-NeRF-360 distortion loss on intervals (DVGO-v2 form)
+    ref = np.zeros(rays_a.shape[0])
+    for ray, start, N in rays_a:
+        w, t, d = ws[start:start + N].astype(np.float64), ts[start:start + N].astype(np.float64), deltas[start:start + N]
+        # the scan form equals sum_{i>j} 2 w_i w_j (t_i - t_j) + sum_i w_i^2 d_i / 3 for sorted t
+        acc = 0.0
+        for i in range(N):
+            for j in range(i):
+                acc += 2 * w[i] * w[j] * (t[i] - t[j])
+        ref[ray] = acc + (w * w * d).sum() / 3
+    # ts of one ray must be sorted for the identity above: _composite_inputs sorts globally -> sorted per ray
+    loss = oracle.distortion_fwd(ws, deltas, ts, rays_a)
+    np.testing.assert_allclose(loss, ref, rtol=2e-4, atol=1e-7)
+    g = rng.standard_normal(rays_a.shape[0]).astype(np.float32)
+    dws = oracle.distortion_bwd(g, ws, deltas, ts, rays_a)
+    eps = 1e-3
+    for s in range(0, S, max(1, S // 25)):
+        wp, wm = ws.copy(), ws.copy()
+        wp[s] += eps
+        wm[s] -= eps
+        fd = ((oracle.distortion_fwd(wp, deltas, ts, rays_a).astype(np.float64) -
+               oracle.distortion_fwd(wm, deltas, ts, rays_a)) * g).sum() / (2 * eps)
+        assert abs(fd - dws[s]) < 2e-3 * max(1.0, abs(fd)), (s, fd, dws[s])
