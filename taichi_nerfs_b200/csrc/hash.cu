@@ -108,6 +108,22 @@ struct Vec2<float> { using type = float2; };
 template <>
 struct Vec2<__half> { using type = __half2; };
 
+// two adjacent table entries as one vector load
+template <typename V2>
+struct Pair;
+template <>
+struct Pair<float2> {
+    using type = float4;
+    __device__ static __forceinline__ float2 lo(const float4& p) { return make_float2(p.x, p.y); }
+    __device__ static __forceinline__ float2 hi(const float4& p) { return make_float2(p.z, p.w); }
+};
+template <>
+struct Pair<__half2> {
+    using type = uint2;
+    __device__ static __forceinline__ __half2 lo(const uint2& p) { return *reinterpret_cast<const __half2*>(&p.x); }
+    __device__ static __forceinline__ __half2 hi(const uint2& p) { return *reinterpret_cast<const __half2*>(&p.y); }
+};
+
 // ---- forward -------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restrict__ xyz,
@@ -146,8 +162,21 @@ __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restr
                 have = true;
                 uint32_t idx[8];
                 corner_indices(m, g, idx);
+                // the two x-neighbours (c, c+1) share one aligned 2-entry block whenever their indices
+                // differ only in bit 0 (always on hashed levels with even gx: h(x+1) = h(x)^1): one load
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + idx[c]);
+                for (int c = 0; c < 8; c += 2) {
+                    if ((idx[c] ^ idx[c + 1]) == 1u) {
+                        using V4 = typename Pair<V2>::type;
+                        const V4 pr = __ldg(reinterpret_cast<const V4*>(tab + (idx[c] & ~1u)));
+                        const V2 lo = Pair<V2>::lo(pr), hi = Pair<V2>::hi(pr);
+                        v[c] = (idx[c] & 1u) ? hi : lo;
+                        v[c + 1] = (idx[c] & 1u) ? lo : hi;
+                    } else {
+                        v[c] = __ldg(tab + idx[c]);
+                        v[c + 1] = __ldg(tab + idx[c + 1]);
+                    }
+                }
                 pg[0] = g[0];
                 pg[1] = g[1];
                 pg[2] = g[2];
@@ -222,7 +251,15 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
         uint32_t idx[8];
         corner_indices(m, pg, idx);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) atomicAdd(g2 + idx[c], acc[c]);  // red.global.add.v2.f32
+        for (int c = 0; c < 8; c += 2) {
+            if ((idx[c] ^ idx[c + 1]) == 1u) {  // x-neighbours in one aligned 16-byte block: one L2 atomic
+                const float2 lo = (idx[c] & 1u) ? acc[c + 1] : acc[c], hi = (idx[c] & 1u) ? acc[c] : acc[c + 1];
+                atomicAdd(reinterpret_cast<float4*>(g2 + (idx[c] & ~1u)), make_float4(lo.x, lo.y, hi.x, hi.y));
+            } else {
+                atomicAdd(g2 + idx[c], acc[c]);  // red.global.add.v2.f32
+                atomicAdd(g2 + idx[c + 1], acc[c + 1]);
+            }
+        }
     };
 #pragma unroll 2
     for (int j = 0; j < kChunk; ++j) {

@@ -52,7 +52,7 @@ constexpr int kDH4 = kH4 + kB64;             // dL/dH4             [128 x 64]
 constexpr int kDO = kDH4 + kB64;             // dL/do (3 of 16)    [128 x 16]
 constexpr int kDH = kDO + kB16;              // dL/dh              [128 x 16]
 constexpr int kBarBwd = kDH + kB16;
-constexpr int kSmemBytesBwd = kBarBwd + 16;  // 110,608 B -> 2 CTAs / SM
+constexpr int kSmemBytesBwd = kBarBwd + 32;  // 110,624 B -> 2 CTAs / SM
 // TMEM columns of the backward kernel: per-tile accumulator + persistent weight-gradient accumulators
 constexpr uint32_t kTmemColsBwd = 256;
 constexpr uint32_t kColDW4 = 64, kColDW1 = 128, kColDW3 = 160, kColDW2T = 192, kColDW5T = 208;
@@ -103,16 +103,30 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread i of warp w = lane 32w+i)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
-    uint32_t r[16];
+// issue only; the registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t r[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    tmem_ld16_issue(taddr, r);
+    tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// all 64 accumulator columns of this thread's row with a single wait (the four loads pipeline)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float v[64]) {
+    uint32_t r[64];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) tmem_ld16_issue(taddr + g * 16, r + g * 16);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // ---- descriptors -------------------------------------------------------------------------------------
@@ -187,16 +201,14 @@ __device__ __forceinline__ void sh16(float x, float y, float z, float* e) {  // 
 
 // hidden-layer epilogue: TMEM [128 x 64] fp32 -> relu -> fp16 -> next operand buffer (K = 64 layout)
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, uint8_t* dst, int row) {
+    float v[64];
+    tmem_ld64(tmem_row, v);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        float v[16];
-        tmem_ld16(tmem_row + g * 16, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-        *reinterpret_cast<uint4*>(dst + chunk_off(row, 2 * g, 64)) =
-            make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        *reinterpret_cast<uint4*>(dst + chunk_off(row, 2 * g + 1, 64)) =
-            make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+    for (int kc = 0; kc < 8; ++kc) {
+        const float* q = v + kc * 8;
+        *reinterpret_cast<uint4*>(dst + chunk_off(row, kc, 64)) =
+            make_uint4(pack_h2(fmaxf(q[0], 0.f), fmaxf(q[1], 0.f)), pack_h2(fmaxf(q[2], 0.f), fmaxf(q[3], 0.f)),
+                       pack_h2(fmaxf(q[4], 0.f), fmaxf(q[5], 0.f)), pack_h2(fmaxf(q[6], 0.f), fmaxf(q[7], 0.f)));
     }
 }
 
@@ -398,24 +410,21 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const Operand& a, co
 // backward hidden epilogue: TMEM [128 x 64] fp32 -> fp16, masked by relu'(act) where `act` holds the
 // post-ReLU forward activation of this thread's row -> dst (K = 64 layout).  dst may alias act.
 __device__ __forceinline__ void epilogue_relu_bwd(uint32_t tmem_row, const uint8_t* act, uint8_t* dst, int row) {
+    float v[64];
+    tmem_ld64(tmem_row, v);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        float v[16];
-        tmem_ld16(tmem_row + g * 16, v);
+    for (int kc = 0; kc < 8; ++kc) {
+        const uint4 a = *reinterpret_cast<const uint4*>(act + chunk_off(row, kc, 64));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+        uint32_t o[4];
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-            const uint4 a = *reinterpret_cast<const uint4*>(act + chunk_off(row, 2 * g + hlf, 64));
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-            uint32_t o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const __half2 ah = *reinterpret_cast<const __half2*>(&aw[j]);
-                const float m0 = __low2float(ah) > 0.0f ? v[hlf * 8 + 2 * j] : 0.0f;
-                const float m1 = __high2float(ah) > 0.0f ? v[hlf * 8 + 2 * j + 1] : 0.0f;
-                o[j] = pack_h2(m0, m1);
-            }
-            *reinterpret_cast<uint4*>(dst + chunk_off(row, 2 * g + hlf, 64)) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int j = 0; j < 4; ++j) {
+            const __half2 ah = *reinterpret_cast<const __half2*>(&aw[j]);
+            const float m0 = __low2float(ah) > 0.0f ? v[kc * 8 + 2 * j] : 0.0f;
+            const float m1 = __high2float(ah) > 0.0f ? v[kc * 8 + 2 * j + 1] : 0.0f;
+            o[j] = pack_h2(m0, m1);
         }
+        *reinterpret_cast<uint4*>(dst + chunk_off(row, kc, 64)) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -427,7 +436,9 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar = smem_u32(smem + kBarBwd);
+    const uint32_t bar2 = smem_u32(smem + kBarBwd + 16);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBarBwd + 8);
+    uint32_t phase2 = 0;
 
     stage_weight(smem + kW1, w.w1, 64, 64, 32);
     stage_weight(smem + kW2, w.w2, 16, 16, 64);
@@ -436,6 +447,7 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
     stage_weight(smem + kW5, w.w5, 3, 16, 64);
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar2, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), kTmemColsBwd);
@@ -453,18 +465,25 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
                    aH3 = smem_u32(smem + kH3), aH4 = smem_u32(smem + kH4), aDH4 = smem_u32(smem + kDH4),
                    aDO = smem_u32(smem + kDO), aDH = smem_u32(smem + kDH);
 
-#define NGP_ROUND(ISSUE)                       \
+// One MMA round.  DX feeds the next epilogue and is committed to `bar`; DW (weight-gradient MMAs, may be
+// empty) is issued right behind it and runs while the epilogue executes.  tcgen05.commit tracks ALL prior
+// MMAs of the issuing thread, so the commit of round r+1 also covers DW of round r: every buffer a DW
+// reads is only overwritten after a later round's wait — except the last round's, which commits to `bar2`.
+#define NGP_ROUND2(DX, DW, LAST)               \
     fence_proxy_async();                       \
     tc_fence_before();                         \
     __syncthreads();                           \
     if (tid == 0) {                            \
         tc_fence_after();                      \
-        ISSUE;                                 \
+        DX;                                    \
         umma_commit(bar);                      \
+        DW;                                    \
+        if (LAST) umma_commit(bar2);           \
     }                                          \
     mbar_wait(bar, phase);                     \
     phase ^= 1;                                \
     tc_fence_after();
+#define NGP_ROUND(ISSUE) NGP_ROUND2(ISSUE, (void)0, false)
 
     bool first = true;  // first tile of this CTA: weight-gradient accumulators start from zero
     const int64_t n_tiles = (n + kTile - 1) / kTile;
@@ -540,19 +559,22 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
 
         // ================= backward =================
         // R1: dH4pre = dO W5 ;  dW5^T += H4^T dO
-        NGP_ROUND(
-            issue_gemm(tmem_base, op_kmajor(aDO, 16), op_mnmajor(aW5, 64), 1, idesc_full(128, 64, 0, 1), false);
-            issue_gemm(tmem_base + kColDW5T, op_mnmajor(aH4, 64), op_mnmajor(aDO, 16), 8, idesc_full(64, 16, 1, 1), !first))
+        NGP_ROUND2(
+            issue_gemm(tmem_base, op_kmajor(aDO, 16), op_mnmajor(aW5, 64), 1, idesc_full(128, 64, 0, 1), false),
+            issue_gemm(tmem_base + kColDW5T, op_mnmajor(aH4, 64), op_mnmajor(aDO, 16), 8, idesc_full(64, 16, 1, 1), !first),
+            false)
         epilogue_relu_bwd(tmem_row, smem + kH4, smem + kDH4, tid);
         // R2: dH3pre = dH4 W4 ;  dW4 += dH4^T H3
-        NGP_ROUND(
-            issue_gemm(tmem_base, op_kmajor(aDH4, 64), op_mnmajor(aW4, 64), 4, idesc_full(128, 64, 0, 1), false);
-            issue_gemm(tmem_base + kColDW4, op_mnmajor(aDH4, 64), op_mnmajor(aH3, 64), 8, idesc_full(64, 64, 1, 1), !first))
+        NGP_ROUND2(
+            issue_gemm(tmem_base, op_kmajor(aDH4, 64), op_mnmajor(aW4, 64), 4, idesc_full(128, 64, 0, 1), false),
+            issue_gemm(tmem_base + kColDW4, op_mnmajor(aDH4, 64), op_mnmajor(aH3, 64), 8, idesc_full(64, 64, 1, 1), !first),
+            false)
         epilogue_relu_bwd(tmem_row, smem + kH3, smem + kH4, tid);      // dH3 -> H4's buffer (H4 is dead)
         // R3: dX3 = dH3 W3 ;  dW3 += dH3^T X3
-        NGP_ROUND(
-            issue_gemm(tmem_base, op_kmajor(aH4, 64), op_mnmajor(aW3, 32), 4, idesc_full(128, 32, 0, 1), false);
-            issue_gemm(tmem_base + kColDW3, op_mnmajor(aH4, 64), op_mnmajor(aX3, 32), 8, idesc_full(64, 32, 1, 1), !first))
+        NGP_ROUND2(
+            issue_gemm(tmem_base, op_kmajor(aH4, 64), op_mnmajor(aW3, 32), 4, idesc_full(128, 32, 0, 1), false),
+            issue_gemm(tmem_base + kColDW3, op_mnmajor(aH4, 64), op_mnmajor(aX3, 32), 8, idesc_full(64, 32, 1, 1), !first),
+            false)
         {
             // dh = dX3[:, 16:32] (+ TruncExp backward on h[:,0], networks.py:26-30), fp16
             float g[16];
@@ -565,14 +587,16 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
                 make_uint4(pack_h2(g[8], g[9]), pack_h2(g[10], g[11]), pack_h2(g[12], g[13]), pack_h2(g[14], g[15]));
         }
         // R4: dH1pre = dh W2 ;  dW2^T += H1^T dh
-        NGP_ROUND(
-            issue_gemm(tmem_base, op_kmajor(aDH, 16), op_mnmajor(aW2, 64), 1, idesc_full(128, 64, 0, 1), false);
-            issue_gemm(tmem_base + kColDW2T, op_mnmajor(aH1, 64), op_mnmajor(aDH, 16), 8, idesc_full(64, 16, 1, 1), !first))
+        NGP_ROUND2(
+            issue_gemm(tmem_base, op_kmajor(aDH, 16), op_mnmajor(aW2, 64), 1, idesc_full(128, 64, 0, 1), false),
+            issue_gemm(tmem_base + kColDW2T, op_mnmajor(aH1, 64), op_mnmajor(aDH, 16), 8, idesc_full(64, 16, 1, 1), !first),
+            false)
         epilogue_relu_bwd(tmem_row, smem + kH1, smem + kH3, tid);      // dH1 -> H3's buffer (H3 is dead)
         // R5: dE = dH1 W1 ;  dW1 += dH1^T E
-        NGP_ROUND(
-            issue_gemm(tmem_base, op_kmajor(aH3, 64), op_mnmajor(aW1, 32), 4, idesc_full(128, 32, 0, 1), false);
-            issue_gemm(tmem_base + kColDW1, op_mnmajor(aH3, 64), op_mnmajor(aE, 32), 8, idesc_full(64, 32, 1, 1), !first))
+        NGP_ROUND2(
+            issue_gemm(tmem_base, op_kmajor(aH3, 64), op_mnmajor(aW1, 32), 4, idesc_full(128, 32, 0, 1), false),
+            issue_gemm(tmem_base + kColDW1, op_mnmajor(aH3, 64), op_mnmajor(aE, 32), 8, idesc_full(64, 32, 1, 1), !first),
+            true)
         {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -595,10 +619,13 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
             }
         }
         first = false;
+        mbar_wait(bar2, phase2);  // dW1 (reads E and dH1) must finish before the next tile restages them
+        phase2 ^= 1;
         tc_fence_before();
         __syncthreads();
     }
 #undef NGP_ROUND
+#undef NGP_ROUND2
 
     // ---- flush the weight-gradient accumulators: M = 64 rows live on TMEM lanes (m%16) + 32*(m/16)
     if (!first) {
