@@ -10,6 +10,7 @@ from .volume_render_test import composite_test
 
 MAX_SAMPLES = 1024
 NEAR_DISTANCE = 0.01
+_FORCE_LOOP = False  # set True to use the reference-shaped incremental loop for test-time rendering
 
 
 def render(model, rays_o, rays_d, test_time=False, exp_step_factor=0, T_threshold=1e-4,
@@ -21,6 +22,10 @@ def render(model, rays_o, rays_d, test_time=False, exp_step_factor=0, T_threshol
     rays_d = rays_d.contiguous()
     hits_t = ray_aabb_intersection(rays_o, rays_d, model.scale)
     if test_time:
+        if getattr(model, '_fusable', None) is not None and model._fusable(rays_o) and not _FORCE_LOOP:
+            # same result as the incremental loop below, without its per-iteration host syncs
+            from taichi_nerfs_b200.render_frame import render_frame
+            return render_frame(model, rays_o, rays_d, exp_step_factor, T_threshold, max_samples)
         return _render_rays_test(model, rays_o, rays_d, hits_t, exp_step_factor, T_threshold, max_samples)
     return _render_rays_train(model, rays_o, rays_d, hits_t, exp_step_factor, T_threshold)
 

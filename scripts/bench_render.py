@@ -30,9 +30,8 @@ def frame():
     with torch.autocast("cuda", dtype=torch.float16):
         directions = get_ray_directions(800, 800, K, device=dev)
         rays_o, rays_d = get_rays(directions, pose)
-        if impl == "fused":
-            from taichi_nerfs_b200.render_frame import render_frame
-            return render_frame(model, rays_o, rays_d)
+        import modules.rendering as R
+        R._FORCE_LOOP = impl == "loop"
         return render(model, rays_o, rays_d, test_time=True)
 
 

@@ -71,3 +71,26 @@ def test_gui_render_cam():
         gui.model.update_density_grid(0.01 * 1024 / 3 ** 0.5, warmup=True)
     img = gui.render_cam()
     assert img.shape == (64, 64, 3) and torch.isfinite(img).all()
+
+
+def test_render_frame_equals_incremental_loop(lego_bitfield):
+    """Batched test-time rendering == the reference-shaped while-loop (chunking must not matter)."""
+    import modules.rendering as R
+    from datasets.ray_utils import get_ray_directions, get_rays
+    from datasets.synthetic import SyntheticLego, hemisphere_poses
+    from modules.networks import NGP
+    torch.manual_seed(1)
+    m = NGP(scale=0.5, max_res=1024, half_opt=True).cuda()
+    with torch.no_grad():
+        m.pos_encoder.hash_table.mul_(4e4)  # dense-ish medium so early termination is exercised
+        m.density_bitfield.copy_(torch.from_numpy(lego_bitfield))
+    K = SyntheticLego(n_images=2, img_wh=(160, 160), focal=222.2).K.cuda()
+    o, d = get_rays(get_ray_directions(160, 160, K, device='cuda'), hemisphere_poses(3)[2].cuda())
+    with torch.autocast('cuda', dtype=torch.float16):
+        R._FORCE_LOOP = True
+        ref = R.render(m, o, d, test_time=True)
+        R._FORCE_LOOP = False
+        got = R.render(m, o, d, test_time=True)
+    assert float(ref['opacity'].max()) > 0.5
+    for k in ('rgb', 'opacity', 'depth'):
+        assert (ref[k] - got[k]).abs().max() < 2e-3, k
