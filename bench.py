@@ -37,6 +37,10 @@ BYTES_PER_SAMPLE = {"hash_fwd": 588, "hash_bwd": 1100, "mlp_fwd": 86, "mlp_bwd":
                     "composite_fwd": 22, "composite_bwd": 32, "march": 32}
 
 
+# DRAM bytes per launch of each kernel from the committed `ncu --set full` capture (profiles/), same workload
+NCU_DRAM_BYTES_PER_LAUNCH = {"hash_bwd": 215.37e6 + 3.66e6, "hash_fwd": 49.69e6 + 99.32e6}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -187,6 +191,17 @@ def run_ours(args):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms)
 
+    if args.ncu_window > 0:
+        for s in range(PREWARM):
+            one_step(1 + s % 8, batches[s % len(batches)])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for s in range(args.ncu_window):
+            one_step(1 + s, batches[s % len(batches)])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+
     # ---- device-resident arm ("value") -------------------------------------------------------------
     clocks = ClockSampler(local)
     if rank == 0:
@@ -307,7 +322,10 @@ def kernel_roofline(torch, ops, model, trainer, ds, get_rays, dev):
     alg_bytes = BYTES_PER_SAMPLE[top] * S
     achieved = alg_bytes / (times[top] * 1e-3) / 1e9
     return {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "samples": S,
+            "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(top), "traffic_unit": "bytes/launch",
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, "
+                              "profiles/r1_ncu_summary_after_hash_march_opt.txt (S=2.19 M samples)",
+            "peak_source": peak_src, "samples": S,
             "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE[top], "kernel_ms": times,
             "note": "fp16 table (21.8 MiB) + fp32 grad (43.6 MiB) fit the 126 MB L2: gathers/atomics are L2-bound, "
                     "so algorithmic GB/s over the HBM peak can exceed 1 (BASELINE.md §5)"}
@@ -403,6 +421,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-rays", type=int, default=256, help="rays per step of the reference arm's bounded sample")
+    ap.add_argument("--ncu-window", type=int, default=0,
+                    help="profiling aid: wrap this many extra steps in cudaProfilerStart/Stop "
+                         "(use with `ncu --profile-from-start off`); numbers printed under ncu are not bench values")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
