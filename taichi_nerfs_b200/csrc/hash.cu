@@ -26,6 +26,8 @@ constexpr int kTile = 512;
 constexpr int kChunk = 16;
 constexpr int kThreads = 512;
 constexpr int kRow = kTile + kTile / kChunk + 1;  // 545 words: chunk stride 17 (conflict-free), odd row stride
+constexpr int kXChunk = kChunk * 3 + 1;           // xyz staging: 49 words per 16-sample chunk -> lanes hit distinct banks
+constexpr int kXWords = (kTile / kChunk) * kXChunk;
 
 struct LevelMeta {
     uint32_t offset;     // entries
@@ -134,12 +136,12 @@ __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restr
     constexpr bool kHalf = sizeof(T) == 2;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float* sx = reinterpret_cast<float*>(smem_raw);                         // [kTile*3]
-    V2* tile = reinterpret_cast<V2*>(smem_raw + kTile * 3 * sizeof(float));  // [L][kRow]
+    V2* tile = reinterpret_cast<V2*>(smem_raw + kXWords * sizeof(float));  // [L][kRow]
 
     const int L = lay.n_levels;
     const int64_t base = (int64_t)blockIdx.x * kTile;
     const int rows = (int)min((int64_t)kTile, n - base);
-    for (int k = threadIdx.x; k < rows * 3; k += kThreads) sx[k] = xyz[base * 3 + k];
+    for (int k = threadIdx.x; k < rows * 3; k += kThreads) sx[k + k / (kChunk * 3)] = xyz[base * 3 + k];
     __syncthreads();
 
     const int level = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -154,7 +156,8 @@ __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restr
         for (int j = 0; j < kChunk; ++j) {
             const int s = lane * kChunk + j;
             if (s >= rows) break;
-            const float x[3] = {sx[s * 3 + 0], sx[s * 3 + 1], sx[s * 3 + 2]};
+            const float* xp = sx + lane * kXChunk + j * 3;
+            const float x[3] = {xp[0], xp[1], xp[2]};
             uint32_t g[3];
             float pos[3];
             grid_pos<kHalf>(x, m, g, pos);
@@ -225,12 +228,12 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
     constexpr bool kHalf = sizeof(T) == 2;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float* sx = reinterpret_cast<float*>(smem_raw);
-    V2* tile = reinterpret_cast<V2*>(smem_raw + kTile * 3 * sizeof(float));
+    V2* tile = reinterpret_cast<V2*>(smem_raw + kXWords * sizeof(float));
 
     const int L = lay.n_levels;
     const int64_t base = (int64_t)blockIdx.x * kTile;
     const int rows = (int)min((int64_t)kTile, n - base);
-    for (int k = threadIdx.x; k < rows * 3; k += kThreads) sx[k] = xyz[base * 3 + k];
+    for (int k = threadIdx.x; k < rows * 3; k += kThreads) sx[k + k / (kChunk * 3)] = xyz[base * 3 + k];
     const V2* d2 = reinterpret_cast<const V2*>(dout) + base * L;
     for (int k = threadIdx.x; k < rows * L; k += kThreads) {
         const int r = k / L, l = k - r * L;
@@ -269,7 +272,8 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
         if constexpr (kHalf) dy = __half22float2(trow[j]);
         else dy = trow[j];
         if (dy.x == 0.0f && dy.y == 0.0f) continue;  // hash_encoder_half.py:210
-        const float x[3] = {sx[s * 3 + 0], sx[s * 3 + 1], sx[s * 3 + 2]};
+        const float* xp = sx + lane * kXChunk + j * 3;
+        const float x[3] = {xp[0], xp[1], xp[2]};
         uint32_t g[3];
         float pos[3];
         grid_pos<kHalf>(x, m, g, pos);
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(256) hash_bwd_input_kernel(const float* __rest
 }
 
 size_t smem_bytes(int n_levels, int vec_bytes) {
-    return (size_t)kTile * 3 * sizeof(float) + (size_t)n_levels * kRow * vec_bytes;
+    return (size_t)kXWords * sizeof(float) + (size_t)n_levels * kRow * vec_bytes;
 }
 
 // the fp32 tiles need more than the default 48 KB of dynamic shared memory (6 KB + 16*545*8 = 74 KB)
