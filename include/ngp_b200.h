@@ -198,6 +198,10 @@ int ngp_distortion_bwd(const float* dL_dloss, const float* ws, const float* delt
 /* replaces packbits, modules/utils.py:157-169 */
 int ngp_packbits(const float* density_grid, float density_threshold,
                  uint8_t* density_bitfield, int64_t n_bytes, void* stream);
+/* same, with the threshold min(*mean_density_dev, density_threshold) taken from device memory so
+ * that NGP.update_density_grid (modules/networks.py:286-290) needs no `.item()` host sync */
+int ngp_packbits_dev(const float* density_grid, const float* mean_density_dev, float density_threshold,
+                     uint8_t* density_bitfield, int64_t n_bytes, void* stream);
 /* replaces morton3D_kernel / morton3D_invert_kernel, modules/utils.py:120-154 */
 int ngp_morton3d(const int32_t* coords, int32_t* indices, int64_t n, void* stream);
 int ngp_morton3d_invert(const int32_t* indices, int32_t* coords, int64_t n, void* stream);

@@ -204,9 +204,13 @@ class NGP(nn.Module):
             decay = torch.clamp(decay ** (1 / self.count_grid), 0.1, 0.95)
         self.density_grid = torch.where(self.density_grid < 0, self.density_grid,
                                         torch.maximum(self.density_grid * decay, tmp))
-        mean_density = self.density_grid[self.density_grid > 0].mean().item()
-        packbits(self.density_grid.reshape(-1).contiguous(), min(mean_density, density_threshold),
-                 self.density_bitfield)
+        # mean over the positive cells, kept on the device: the reference's `.mean().item()` (:286) is a
+        # host sync every 16th step; the threshold min(mean, density_threshold) is applied inside the kernel
+        positive = self.density_grid > 0
+        mean_density = (self.density_grid * positive).sum() / positive.sum()
+        from taichi_nerfs_b200 import ops
+        ops.packbits(self.density_grid.reshape(-1).contiguous(), density_threshold, self.density_bitfield,
+                     mean_dev=mean_density.reshape(1))
 
 
 def _fused_mlp_available() -> bool:

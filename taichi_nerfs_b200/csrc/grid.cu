@@ -22,9 +22,14 @@ __device__ __forceinline__ int32_t compact_bits(uint32_t x) {  // utils.py:110-1
 
 // one thread per output byte; the 8 floats it tests are two aligned float4 loads
 __global__ void __launch_bounds__(256) packbits_kernel(const float* __restrict__ grid, float thr,
+                                                       const float* __restrict__ mean_dev,
                                                        uint8_t* __restrict__ bits, int64_t n_bytes) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_bytes) return;
+    if (mean_dev != nullptr) {  // python: min(mean_density, density_threshold) -> NaN mean stays NaN
+        const float m = *mean_dev;
+        thr = (thr < m) ? thr : m;
+    }
     const float4 a = reinterpret_cast<const float4*>(grid)[2 * n];
     const float4 b = reinterpret_cast<const float4*>(grid)[2 * n + 1];
     uint32_t v = 0;
@@ -68,7 +73,19 @@ int ngp_packbits(const float* density_grid, float density_threshold, uint8_t* de
     NGP_REQUIRE(density_grid && density_bitfield, "null pointer");
     NGP_REQUIRE((reinterpret_cast<uintptr_t>(density_grid) & 15) == 0, "density_grid must be 16-byte aligned");
     packbits_kernel<<<(unsigned)((n_bytes + 255) / 256), 256, 0, ngp::as_stream(stream)>>>(
-        density_grid, density_threshold, density_bitfield, n_bytes);
+        density_grid, density_threshold, nullptr, density_bitfield, n_bytes);
+    NGP_LAUNCHED("packbits_kernel");
+    return 0;
+}
+
+int ngp_packbits_dev(const float* density_grid, const float* mean_density_dev, float density_threshold,
+                     uint8_t* density_bitfield, int64_t n_bytes, void* stream) {
+    NGP_REQUIRE(n_bytes >= 0, "negative n_bytes");
+    if (n_bytes == 0) return 0;
+    NGP_REQUIRE(density_grid && density_bitfield && mean_density_dev, "null pointer");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(density_grid) & 15) == 0, "density_grid must be 16-byte aligned");
+    packbits_kernel<<<(unsigned)((n_bytes + 255) / 256), 256, 0, ngp::as_stream(stream)>>>(
+        density_grid, density_threshold, mean_density_dev, density_bitfield, n_bytes);
     NGP_LAUNCHED("packbits_kernel");
     return 0;
 }

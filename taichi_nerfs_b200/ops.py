@@ -180,10 +180,16 @@ def distortion_bwd(dL_dloss, ws, deltas, ts, rays_a):
 
 
 # ---- occupancy grid helpers ------------------------------------------------------------------------
-def packbits(density_grid, threshold, bitfield):
+def packbits(density_grid, threshold, bitfield, mean_dev=None):
+    """bit i of byte n = grid[8n+i] > thr, thr = threshold or min(*mean_dev, threshold) read on the device."""
     _need_cuda(density_grid, bitfield)
-    check(load().ngp_packbits(_ptr(density_grid), float(threshold), _ptr(bitfield), bitfield.shape[0], _stream()),
-          "packbits")
+    if mean_dev is None:
+        check(load().ngp_packbits(_ptr(density_grid), float(threshold), _ptr(bitfield), bitfield.shape[0], _stream()),
+              "packbits")
+    else:
+        m = mean_dev.float().contiguous()
+        check(load().ngp_packbits_dev(_ptr(density_grid), _ptr(m), float(threshold), _ptr(bitfield),
+                                      bitfield.shape[0], _stream()), "packbits_dev")
 
 
 def morton3d(coords):

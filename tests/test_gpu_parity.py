@@ -416,3 +416,14 @@ def test_distortion_loss(ops, oracle):
     distortion_loss({'ws': w, 'deltas': T(deltas), 'ts': T(ts), 'rays_a': T(rays_a)}).mean().backward()
     assert np.abs(N(w.grad) - oracle.distortion_bwd(np.full(rays_a.shape[0], 1 / rays_a.shape[0], np.float32),
                                                     ws, deltas, ts, rays_a)).max() <= 1e-3 * np.abs(N(w.grad)).max()
+
+
+def test_packbits_device_threshold(ops, oracle):
+    rng = np.random.default_rng(37)
+    grid = rng.standard_normal(128 ** 3).astype(np.float32)
+    for mean, thr in ((0.3, 5.9), (7.0, 5.9), (float('nan'), 5.9)):
+        bits = torch.full((128 ** 3 // 8,), 255, device=DEV, dtype=torch.uint8)
+        ops.packbits(T(grid), thr, bits, mean_dev=torch.tensor([mean], device=DEV))
+        eff = min(mean, thr)  # python semantics of networks.py:288-290 (NaN mean -> NaN threshold -> no bits)
+        want = oracle.packbits(grid, eff) if eff == eff else np.zeros(128 ** 3 // 8, np.uint8)
+        assert np.array_equal(N(bits), want)
