@@ -135,6 +135,38 @@ int ngp_hash_encode_bwd_input(const float* xyz, const void* table, const void* d
                               const ngp_hash_layout* layout, float* dx,
                               int64_t n, void* stream);
 
+/* ---- sync-free ("_dyn") variants used by the graph-captured training step -------------------
+ * Same kernels as above, but the number of valid rows is read ON THE DEVICE: rows [0, min(n_max,*n_dev))
+ * are processed, so a step can be enqueued (or replayed as a CUDA graph) without the host read-back of
+ * the sample counter that the reference performs at modules/ray_march.py:187-192.
+ * `aabb6` (HOST pointer, 6 floats: xyz_min[3], xyz_max-xyz_min[3]; may be NULL) folds NGP.density's
+ * normalisation x = (x - xyz_min)/(xyz_max - xyz_min) (modules/networks.py:144) into the gather. */
+int ngp_hash_encode_fwd_dyn(const float* xyz, const void* table, const ngp_hash_layout* layout, void* out,
+                            int dtype, int64_t n_max, const int32_t* n_dev, const float* aabb6, void* stream);
+int ngp_hash_encode_bwd_dyn(const float* xyz, const void* dout, int dout_dtype, const ngp_hash_layout* layout,
+                            float* grad_table, int64_t n_max, const int32_t* n_dev, const float* aabb6,
+                            void* stream);
+int ngp_mlp_fwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
+                    void* rgbs_f16, int64_t n_max, const int32_t* n_dev, void* stream);
+int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w,
+                    const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n_max,
+                    const int32_t* n_dev, void* stream);
+/* Adam with the per-step scalars in device memory: hyper_dev = {lr/(1-beta1^t), sqrt(1-beta2^t), inv_scale}
+ * (so the launch arguments are step-invariant and the launch can live in a CUDA graph). */
+int ngp_adam_step_dyn(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_f16_or_null,
+                      const int32_t* found_inf_or_null, const float* hyper_dev, float beta1, float beta2,
+                      float eps, int zero_grad, int64_t n, void* stream);
+/* Advances the device-side step counter and writes hyper_dev for ngp_adam_step_dyn:
+ * lr = cosine annealing from lr0 to lr_min over max_steps (train.py:159-163) evaluated at the 0-based step,
+ * Adam bias corrections for t = step+1 (train.py:143-156). */
+int ngp_adam_hyper_update(int32_t* step_dev, float lr0, float lr_min, int32_t max_steps, float beta1,
+                          float beta2, float inv_scale, float* hyper_dev, void* stream);
+/* per-ray loss head: out = rgb + bg*(1-opacity) (modules/rendering.py:219-226), loss = mean((out-gt)^2)
+ * (train.py:193), and d(loss*loss_scale)/d rgb, /d opacity in one launch.  *loss_sum accumulates
+ * sum((out-gt)^2) (caller zeroes it; divide by 3*n_rays). */
+int ngp_mse_loss_grad(const float* rgb, const float* opacity, const float* gt, float bg, float loss_scale,
+                      float* loss_sum, float* g_rgb, float* g_opacity, int64_t n_rays, void* stream);
+
 /* ---- a6: spherical-harmonics direction encoding -------------------------- */
 /* replaces dir_encoder, modules/spherical_harmonics.py:7-42 */
 int ngp_dir_encode(const float* dirs, float* out, int64_t n, void* stream);

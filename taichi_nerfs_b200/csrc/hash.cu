@@ -29,6 +29,18 @@ constexpr int kRow = kTile + kTile / kChunk + 1;  // 545 words: chunk stride 17 
 constexpr int kXChunk = kChunk * 3 + 1;           // xyz staging: 49 words per 16-sample chunk -> lanes hit distinct banks
 constexpr int kXWords = (kTile / kChunk) * kXChunk;
 
+// optional run-time extras: device-side row count and the world->[0,1] normalisation of NGP.density
+struct Dyn {
+    const int32_t* n_dev;  // rows = min(n, *n_dev) when non-null
+    float lo[3], span[3];
+    int normalize;
+};
+__device__ __forceinline__ int64_t effective_n(const Dyn& dyn, int64_t n) {
+    if (dyn.n_dev == nullptr) return n;
+    const int64_t v = (int64_t)*dyn.n_dev;
+    return v < n ? (v < 0 ? 0 : v) : n;
+}
+
 struct LevelMeta {
     uint32_t offset;     // entries
     uint32_t size;       // entries
@@ -131,8 +143,9 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restrict__ xyz,
                                                             const T* __restrict__ table,
                                                             const __grid_constant__ ngp_hash_layout lay,
-                                                            T* __restrict__ out, int64_t n) {
+                                                            T* __restrict__ out, int64_t n_max, const Dyn dyn) {
     using V2 = typename Vec2<T>::type;
+    const int64_t n = effective_n(dyn, n_max);
     constexpr bool kHalf = sizeof(T) == 2;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float* sx = reinterpret_cast<float*>(smem_raw);                         // [kTile*3]
@@ -140,8 +153,13 @@ __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restr
 
     const int L = lay.n_levels;
     const int64_t base = (int64_t)blockIdx.x * kTile;
+    if (base >= n) return;
     const int rows = (int)min((int64_t)kTile, n - base);
-    for (int k = threadIdx.x; k < rows * 3; k += kThreads) sx[k + k / (kChunk * 3)] = xyz[base * 3 + k];
+    for (int k = threadIdx.x; k < rows * 3; k += kThreads) {
+        float v = xyz[base * 3 + k];
+        if (dyn.normalize) v = f_div(f_sub(v, dyn.lo[k % 3]), dyn.span[k % 3]);  // networks.py:144
+        sx[k + k / (kChunk * 3)] = v;
+    }
     __syncthreads();
 
     const int level = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -223,8 +241,10 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restrict__ xyz,
                                                             const T* __restrict__ dout,
                                                             const __grid_constant__ ngp_hash_layout lay,
-                                                            float* __restrict__ grad_table, int64_t n) {
+                                                            float* __restrict__ grad_table, int64_t n_max,
+                                                            const Dyn dyn) {
     using V2 = typename Vec2<T>::type;
+    const int64_t n = effective_n(dyn, n_max);
     constexpr bool kHalf = sizeof(T) == 2;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float* sx = reinterpret_cast<float*>(smem_raw);
@@ -232,8 +252,13 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
 
     const int L = lay.n_levels;
     const int64_t base = (int64_t)blockIdx.x * kTile;
+    if (base >= n) return;
     const int rows = (int)min((int64_t)kTile, n - base);
-    for (int k = threadIdx.x; k < rows * 3; k += kThreads) sx[k + k / (kChunk * 3)] = xyz[base * 3 + k];
+    for (int k = threadIdx.x; k < rows * 3; k += kThreads) {
+        float v = xyz[base * 3 + k];
+        if (dyn.normalize) v = f_div(f_sub(v, dyn.lo[k % 3]), dyn.span[k % 3]);  // networks.py:144
+        sx[k + k / (kChunk * 3)] = v;
+    }
     const V2* d2 = reinterpret_cast<const V2*>(dout) + base * L;
     for (int k = threadIdx.x; k < rows * L; k += kThreads) {
         const int r = k / L, l = k - r * L;
@@ -364,6 +389,17 @@ int configure_smem() {
     return 0;
 }
 
+Dyn make_dyn(const int32_t* n_dev, const float* aabb6) {
+    Dyn d;
+    d.n_dev = n_dev;
+    d.normalize = aabb6 != nullptr;
+    for (int k = 0; k < 3; ++k) {
+        d.lo[k] = aabb6 ? aabb6[k] : 0.0f;
+        d.span[k] = aabb6 ? aabb6[3 + k] : 1.0f;
+    }
+    return d;
+}
+
 int check_layout(const ngp_hash_layout* lay) {
     NGP_REQUIRE(lay != nullptr, "null layout");
     NGP_REQUIRE(lay->n_levels >= 1 && lay->n_levels <= NGP_MAX_LEVELS, "n_levels out of range");
@@ -377,6 +413,12 @@ extern "C" {
 
 int ngp_hash_encode_fwd(const float* xyz, const void* table, const ngp_hash_layout* layout, void* out,
                         int dtype, int64_t n, void* stream) {
+    return ngp_hash_encode_fwd_dyn(xyz, table, layout, out, dtype, n, nullptr, nullptr, stream);
+}
+
+int ngp_hash_encode_fwd_dyn(const float* xyz, const void* table, const ngp_hash_layout* layout, void* out,
+                            int dtype, int64_t n, const int32_t* n_dev, const float* aabb6, void* stream) {
+    const Dyn dyn = make_dyn(n_dev, aabb6);
     if (int rc = check_layout(layout)) return rc;
     NGP_REQUIRE(n >= 0, "negative n");
     NGP_REQUIRE(dtype == NGP_F32 || dtype == NGP_F16, "bad dtype");
@@ -386,15 +428,21 @@ int ngp_hash_encode_fwd(const float* xyz, const void* table, const ngp_hash_layo
     cudaStream_t st = ngp::as_stream(stream);
     if (int rc = configure_smem()) return rc;
     if (dtype == NGP_F16)
-        hash_fwd_kernel<__half><<<grid, kThreads, smem_bytes(layout->n_levels, 4), st>>>(xyz, (const __half*)table, *layout, (__half*)out, n);
+        hash_fwd_kernel<__half><<<grid, kThreads, smem_bytes(layout->n_levels, 4), st>>>(xyz, (const __half*)table, *layout, (__half*)out, n, dyn);
     else
-        hash_fwd_kernel<float><<<grid, kThreads, smem_bytes(layout->n_levels, 8), st>>>(xyz, (const float*)table, *layout, (float*)out, n);
+        hash_fwd_kernel<float><<<grid, kThreads, smem_bytes(layout->n_levels, 8), st>>>(xyz, (const float*)table, *layout, (float*)out, n, dyn);
     NGP_LAUNCHED("hash_fwd_kernel");
     return 0;
 }
 
 int ngp_hash_encode_bwd(const float* xyz, const void* dout, int dout_dtype, const ngp_hash_layout* layout,
                         float* grad_table, int64_t n, void* stream) {
+    return ngp_hash_encode_bwd_dyn(xyz, dout, dout_dtype, layout, grad_table, n, nullptr, nullptr, stream);
+}
+
+int ngp_hash_encode_bwd_dyn(const float* xyz, const void* dout, int dout_dtype, const ngp_hash_layout* layout,
+                            float* grad_table, int64_t n, const int32_t* n_dev, const float* aabb6, void* stream) {
+    const Dyn dyn = make_dyn(n_dev, aabb6);
     if (int rc = check_layout(layout)) return rc;
     NGP_REQUIRE(n >= 0, "negative n");
     NGP_REQUIRE(dout_dtype == NGP_F32 || dout_dtype == NGP_F16, "bad dtype");
@@ -405,9 +453,9 @@ int ngp_hash_encode_bwd(const float* xyz, const void* dout, int dout_dtype, cons
     cudaStream_t st = ngp::as_stream(stream);
     if (int rc = configure_smem()) return rc;
     if (dout_dtype == NGP_F16)
-        hash_bwd_kernel<__half><<<grid, kThreads, smem_bytes(layout->n_levels, 4), st>>>(xyz, (const __half*)dout, *layout, grad_table, n);
+        hash_bwd_kernel<__half><<<grid, kThreads, smem_bytes(layout->n_levels, 4), st>>>(xyz, (const __half*)dout, *layout, grad_table, n, dyn);
     else
-        hash_bwd_kernel<float><<<grid, kThreads, smem_bytes(layout->n_levels, 8), st>>>(xyz, (const float*)dout, *layout, grad_table, n);
+        hash_bwd_kernel<float><<<grid, kThreads, smem_bytes(layout->n_levels, 8), st>>>(xyz, (const float*)dout, *layout, grad_table, n, dyn);
     NGP_LAUNCHED("hash_bwd_kernel");
     return 0;
 }

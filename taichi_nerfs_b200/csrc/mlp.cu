@@ -215,8 +215,10 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, uint8_t* dst,
 template <typename TEmb>
 __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
                                                            ngp_mlp_weights w, float* __restrict__ sigmas,
-                                                           __half* __restrict__ rgbs, int64_t n) {
+                                                           __half* __restrict__ rgbs, int64_t n_max,
+                                                           const int32_t* __restrict__ n_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
+    const int64_t n = n_dev ? min(n_max, max((int64_t)*n_dev, (int64_t)0)) : n_max;
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t bar = smem_u32(smem + kBar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBar + 8);
@@ -432,8 +434,10 @@ template <typename TEmb>
 __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
                                                            ngp_mlp_weights w, const float* __restrict__ dsigmas,
                                                            const __half* __restrict__ drgbs, TEmb* __restrict__ demb,
-                                                           float* __restrict__ grad_w, int64_t n) {
+                                                           float* __restrict__ grad_w, int64_t n_max,
+                                                           const int32_t* __restrict__ n_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
+    const int64_t n = n_dev ? min(n_max, max((int64_t)*n_dev, (int64_t)0)) : n_max;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar = smem_u32(smem + kBarBwd);
     const uint32_t bar2 = smem_u32(smem + kBarBwd + 16);
@@ -670,7 +674,7 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
 
 template <typename TEmb>
 int launch_bwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, const float* dsigmas, const void* drgbs,
-               void* demb, float* grad_w, int64_t n, cudaStream_t st) {
+               void* demb, float* grad_w, int64_t n, const int32_t* n_dev, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel<TEmb>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesBwd);
@@ -684,14 +688,14 @@ int launch_bwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, con
     const int64_t max_ctas = (int64_t)ngp::sm_count() * 2;  // 108 KB smem + 256 TMEM columns per CTA
     const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
     mlp_bwd_kernel<TEmb><<<grid, kThreads, kSmemBytesBwd, st>>>((const TEmb*)emb, dirs, *w, dsigmas, (const __half*)drgbs,
-                                                               (TEmb*)demb, grad_w, n);
+                                                               (TEmb*)demb, grad_w, n, n_dev);
     NGP_LAUNCHED("mlp_bwd_kernel");
     return 0;
 }
 
 template <typename TEmb>
 int launch_fwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, float* sigmas, void* rgbs, int64_t n,
-               cudaStream_t st) {
+               const int32_t* n_dev, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel<TEmb>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -704,7 +708,7 @@ int launch_fwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, flo
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int64_t max_ctas = (int64_t)ngp::sm_count() * 4;  // 52 KB smem + 64 TMEM columns per CTA
     const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
-    mlp_fwd_kernel<TEmb><<<grid, kThreads, kSmemBytes, st>>>((const TEmb*)emb, dirs, *w, sigmas, (__half*)rgbs, n);
+    mlp_fwd_kernel<TEmb><<<grid, kThreads, kSmemBytes, st>>>((const TEmb*)emb, dirs, *w, sigmas, (__half*)rgbs, n, n_dev);
     NGP_LAUNCHED("mlp_fwd_kernel");
     return 0;
 }
@@ -721,6 +725,11 @@ int64_t ngp_mlp_save_bytes(int64_t n) {
 int ngp_mlp_fwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
                 void* rgbs_f16, void* save, int64_t n, void* stream) {
     (void)save;
+    return ngp_mlp_fwd_dyn(emb, emb_dtype, dirs, w, sigmas, rgbs_f16, n, nullptr, stream);
+}
+
+int ngp_mlp_fwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
+                    void* rgbs_f16, int64_t n, const int32_t* n_dev, void* stream) {
     NGP_REQUIRE(n >= 0, "negative n");
     NGP_REQUIRE(emb_dtype == NGP_F32 || emb_dtype == NGP_F16, "bad dtype");
     if (n == 0) return 0;
@@ -732,13 +741,18 @@ int ngp_mlp_fwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp
                           reinterpret_cast<uintptr_t>(w->w5);
     NGP_REQUIRE((wal & 15) == 0, "weights must be 16-byte aligned");
     cudaStream_t st = ngp::as_stream(stream);
-    if (emb_dtype == NGP_F16) return launch_fwd<__half>(emb, dirs, w, sigmas, rgbs_f16, n, st);
-    return launch_fwd<float>(emb, dirs, w, sigmas, rgbs_f16, n, st);
+    if (emb_dtype == NGP_F16) return launch_fwd<__half>(emb, dirs, w, sigmas, rgbs_f16, n, n_dev, st);
+    return launch_fwd<float>(emb, dirs, w, sigmas, rgbs_f16, n, n_dev, st);
 }
 
 int ngp_mlp_bwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
                 const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n, void* stream) {
     (void)save;
+    return ngp_mlp_bwd_dyn(emb, emb_dtype, dirs, w, dsigmas, drgbs_f16, demb, grad_w, n, nullptr, stream);
+}
+
+int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const float* dsigmas,
+                    const void* drgbs_f16, void* demb, float* grad_w, int64_t n, const int32_t* n_dev, void* stream) {
     NGP_REQUIRE(n >= 0, "negative n");
     NGP_REQUIRE(emb_dtype == NGP_F32 || emb_dtype == NGP_F16, "bad dtype");
     if (n == 0) return 0;
@@ -751,8 +765,8 @@ int ngp_mlp_bwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp
                           reinterpret_cast<uintptr_t>(w->w5);
     NGP_REQUIRE((wal & 15) == 0, "weights must be 16-byte aligned");
     cudaStream_t st = ngp::as_stream(stream);
-    if (emb_dtype == NGP_F16) return launch_bwd<__half>(emb, dirs, w, dsigmas, drgbs_f16, demb, grad_w, n, st);
-    return launch_bwd<float>(emb, dirs, w, dsigmas, drgbs_f16, demb, grad_w, n, st);
+    if (emb_dtype == NGP_F16) return launch_bwd<__half>(emb, dirs, w, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st);
+    return launch_bwd<float>(emb, dirs, w, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st);
 }
 
 }  // extern "C"

@@ -29,8 +29,13 @@ __device__ __forceinline__ void adam1(float& p, float& g, float& m, float& v, co
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, float* __restrict__ grad,
                                                    float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                                    __half* __restrict__ shadow, const int32_t* __restrict__ found_inf,
-                                                   AdamArgs a, int64_t n) {
+                                                   const float* __restrict__ hyper_dev, AdamArgs a, int64_t n) {
     const bool skip = found_inf != nullptr && *found_inf != 0;
+    if (hyper_dev != nullptr) {  // per-step scalars from device memory (graph-captured step)
+        a.lr_over_bc1 = hyper_dev[0];
+        a.bc2_sqrt = hyper_dev[1];
+        a.inv_scale = hyper_dev[2];
+    }
     const int64_t n4 = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -68,6 +73,20 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, fl
         }
         if (a.zero_grad) grad[i] = 0.0f;
     }
+}
+
+__global__ void adam_hyper_kernel(int32_t* __restrict__ step_dev, float lr0, float lr_min, int32_t max_steps, float beta1,
+                                  float beta2, float inv_scale, float* __restrict__ hyper) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int32_t s = *step_dev;  // 0-based index of the step being taken
+    const double frac = (double)min(s, max_steps) / (double)max(max_steps, 1);
+    const double lr = (double)lr_min + ((double)lr0 - (double)lr_min) * (1.0 + cos(3.14159265358979323846 * frac)) / 2.0;
+    const double t = (double)(s + 1);
+    const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+    hyper[0] = (float)(lr / bc1);
+    hyper[1] = (float)sqrt(bc2);
+    hyper[2] = inv_scale;
+    *step_dev = s + 1;
 }
 
 __global__ void __launch_bounds__(256) check_finite_kernel(const float* __restrict__ grad, int64_t n,
@@ -114,8 +133,44 @@ int ngp_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
     const int64_t max_blocks = (int64_t)ngp::sm_count() * 8;
     const unsigned grid = (unsigned)min((work + 255) / 256, max_blocks);
     adam_kernel<<<grid, 256, 0, ngp::as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, (__half*)param_f16_or_null,
-                                                          found_inf_or_null, a, n);
+                                                          found_inf_or_null, nullptr, a, n);
     NGP_LAUNCHED("adam_kernel");
+    return 0;
+}
+
+int ngp_adam_step_dyn(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_f16_or_null,
+                      const int32_t* found_inf_or_null, const float* hyper_dev, float beta1, float beta2, float eps,
+                      int zero_grad, int64_t n, void* stream) {
+    NGP_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return 0;
+    NGP_REQUIRE(param && grad && exp_avg && exp_avg_sq && hyper_dev, "null pointer");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+                         reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq);
+    NGP_REQUIRE((al & 15) == 0, "param/grad/state must be 16-byte aligned");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(param_f16_or_null) & 7) == 0, "fp16 shadow must be 8-byte aligned");
+    AdamArgs a;
+    a.lr_over_bc1 = 0.f;
+    a.bc2_sqrt = 1.f;
+    a.inv_scale = 1.f;
+    a.beta1 = beta1;
+    a.beta2 = beta2;
+    a.eps = eps;
+    a.zero_grad = zero_grad;
+    const int64_t work = (n + 3) / 4;
+    const int64_t max_blocks = (int64_t)ngp::sm_count() * 8;
+    const unsigned grid = (unsigned)min((work + 255) / 256, max_blocks);
+    adam_kernel<<<grid, 256, 0, ngp::as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, (__half*)param_f16_or_null,
+                                                          found_inf_or_null, hyper_dev, a, n);
+    NGP_LAUNCHED("adam_kernel");
+    return 0;
+}
+
+int ngp_adam_hyper_update(int32_t* step_dev, float lr0, float lr_min, int32_t max_steps, float beta1, float beta2,
+                          float inv_scale, float* hyper_dev, void* stream) {
+    NGP_REQUIRE(step_dev && hyper_dev, "null pointer");
+    adam_hyper_kernel<<<1, 32, 0, ngp::as_stream(stream)>>>(step_dev, lr0, lr_min, max_steps, beta1, beta2, inv_scale,
+                                                            hyper_dev);
+    NGP_LAUNCHED("adam_hyper_kernel");
     return 0;
 }
 

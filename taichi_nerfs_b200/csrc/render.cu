@@ -265,6 +265,32 @@ composite_test_kernel(const float* __restrict__ sigmas, const TRgb* __restrict__
     opacity[ray] += op;
 }
 
+// ---- per-ray loss head ------------------------------------------------------------------------------------
+// out = rgb + bg (1 - opacity) (rendering.py:219-226); loss = mean((out - gt)^2) (train.py:193);
+// gradients of loss*loss_scale wrt the compositing outputs, in one launch instead of ~8 torch ops.
+__global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ opacity,
+                                                            const float* __restrict__ gt, float bg, float coef,
+                                                            float* __restrict__ loss_sum, float* __restrict__ g_rgb,
+                                                            float* __restrict__ g_op, int64_t n_rays) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float sq = 0.f;
+    if (r < n_rays) {
+        const float keep = bg * (1.0f - opacity[r]);
+        float gsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float diff = rgb[r * 3 + c] + keep - gt[r * 3 + c];
+            sq += diff * diff;
+            const float g = coef * diff;  // coef = loss_scale * 2 / (3 n_rays)
+            g_rgb[r * 3 + c] = g;
+            gsum += g;
+        }
+        g_op[r] = -bg * gsum;
+    }
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0 && sq != 0.f) atomicAdd(loss_sum, sq);
+}
+
 // ---- distortion loss (Mip-NeRF 360), modules/distortion.py:15-119 -----------------------------------
 // warp per ray; per-ray scans of w and w*t are warp prefix sums carried across 32-sample chunks
 // (the reference's TODO at distortion.py:4-6 asks for exactly this shared/warp scan).
@@ -335,6 +361,18 @@ distortion_bwd_kernel(const float* __restrict__ dL_dloss, const float* __restric
 }  // namespace
 
 extern "C" {
+
+int ngp_mse_loss_grad(const float* rgb, const float* opacity, const float* gt, float bg, float loss_scale,
+                      float* loss_sum, float* g_rgb, float* g_opacity, int64_t n_rays, void* stream) {
+    NGP_REQUIRE(n_rays >= 0, "negative n_rays");
+    if (n_rays == 0) return 0;
+    NGP_REQUIRE(rgb && opacity && gt && loss_sum && g_rgb && g_opacity, "null pointer");
+    const float coef = loss_scale * 2.0f / (3.0f * (float)n_rays);
+    mse_loss_grad_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, ngp::as_stream(stream)>>>(
+        rgb, opacity, gt, bg, coef, loss_sum, g_rgb, g_opacity, n_rays);
+    NGP_LAUNCHED("mse_loss_grad_kernel");
+    return 0;
+}
 
 int ngp_distortion_fwd(const float* ws, const float* deltas, const float* ts, const int32_t* rays_a, float* loss,
                        int64_t n_rays, int64_t n_samples, void* stream) {

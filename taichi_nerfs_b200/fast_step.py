@@ -1,0 +1,190 @@
+"""The training step as ONE CUDA graph (no autograd, no host synchronisation, no per-step allocation).
+
+Same math as NGPTrainer.step / the reference's loop body (train.py:184-201) — every stage is one of
+the C-ABI kernels, enqueued in a fixed order on fixed buffers:
+
+  ray_aabb -> march count/scan/write (capacity buffers) -> hash fwd (+AABB normalisation) -> tcgen05 MLP
+  fwd -> composite fwd -> loss head (MSE + bg) -> composite bwd -> MLP bwd -> hash bwd -> [all-reduce]
+  -> check_finite -> device-side LR/bias-correction update -> fused Adam (+fp16 shadow, grad zero)
+
+What makes it graph-capturable: the number of samples S stays on the device (kernels read it from the
+march counter; buffers are sized for `capacity` rows and rays that would overflow are dropped and
+counted), and the per-step optimizer scalars live in device memory.  The reference synchronises the
+host on S every step (modules/ray_march.py:187-192) and inside GradScaler.step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, parallel
+from ._lib import F16, F32, check, load
+from .fused_mlp import mlp_weights
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class StaticTrainStep:
+    def __init__(self, trainer, n_rays: int, samples_per_ray_capacity: int = 384, exp_step_factor: float = 0.0,
+                 T_threshold: float = 1e-4, max_samples: int = 1024, use_graph: bool = True):
+        self.tr = trainer
+        m = self.model = trainer.model
+        enc = m.pos_encoder
+        if not m._fusable(next(m.parameters())):
+            raise _lib.NgpError("StaticTrainStep needs the stock NGP architecture (fused MLP)")
+        dev = next(m.parameters()).device
+        self.dev, self.n = dev, int(n_rays)
+        self.cap = C_ = int(n_rays) * int(samples_per_ray_capacity)
+        self.esf, self.T_thr, self.max_samples = float(exp_step_factor), float(T_threshold), int(max_samples)
+        self.half = hasattr(enc, "table_f16")
+        edt = torch.float16 if self.half else torch.float32
+        f32, i32 = torch.float32, torch.int32
+        z = lambda *s, dtype=f32: torch.zeros(*s, device=dev, dtype=dtype)  # noqa: E731
+        # static inputs
+        self.rays_o, self.rays_d, self.gt, self.noise = z(self.n, 3), z(self.n, 3), z(self.n, 3), z(self.n)
+        # marching
+        self.hits, self.counter, self.rays_a = z(self.n, 2), z(2, dtype=i32), z(self.n, 3, dtype=i32)
+        self.xyzs, self.dirs, self.deltas, self.ts = z(C_, 3), z(C_, 3), z(C_), z(C_)
+        # network
+        self.emb, self.demb = z(C_, 32, dtype=edt), z(C_, 32, dtype=edt)
+        self.sig, self.dsig = z(C_), z(C_)
+        self.rgbs, self.drgbs = z(C_, 3, dtype=torch.float16), z(C_, 3, dtype=torch.float16)
+        # compositing / loss
+        self.total, self.opacity, self.depth, self.rgb = z(self.n, dtype=i32), z(self.n), z(self.n), z(self.n, 3)
+        self.ws = z(C_)
+        self.g_rgb, self.g_op, self.g_depth = z(self.n, 3), z(self.n), z(self.n)
+        self.loss_sum = z(1)
+        # optimizer scalars on the device
+        self.step_dev = torch.full((1,), trainer.step_count, device=dev, dtype=i32)
+        self.hyper = z(3)
+        self.aabb6 = (C.c_float * 6)(*[float(v) for v in m.xyz_min.flatten().tolist()],
+                                     *[float(v) for v in (m.xyz_max - m.xyz_min).flatten().tolist()])
+        self._clayout = enc._clayout
+        self._w_keep = [w.detach() for w in mlp_weights(m)]
+        self._wst = _lib.MlpWeights(*[w.data_ptr() for w in self._w_keep])
+        self.P = enc.total_param_size
+        assert trainer.slices[0] == (0, self.P), "hash table must be the first parameter"
+        offs = [o for o, _ in trainer.slices[1:]]
+        assert offs == [self.P, self.P + 2048, self.P + 3072, self.P + 5120, self.P + 9216], offs
+        # valid placeholder rays (an all-zero direction would march forever, in the reference too)
+        self.rays_o[:] = torch.tensor([1.2, 0.3, 0.5], device=dev)
+        jitter = (torch.arange(self.n, device=dev, dtype=f32)[:, None] % 97) * 1e-3
+        self.rays_d[:] = -self.rays_o + jitter * torch.tensor([0.3, -0.2, 0.1], device=dev)
+        self.graph = None
+        self.use_graph = use_graph and parallel.world_info(trainer.pg)[1] == 1
+        if self.use_graph:
+            self._capture()
+
+    # ---------------------------------------------------------------------------------------------
+    def _st(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _table(self):
+        return self.tr._shadow if self.half else self.model.pos_encoder.hash_table.data
+
+    def _enqueue_forward_backward(self):
+        L, m, st, n, cap = load(), self.model, self._st(), self.n, self.cap
+        tag = F16 if self.half else F32
+        bits = m.density_bitfield
+        check(L.ngp_ray_aabb_intersect(_p(self.rays_o), _p(self.rays_d), float(m.scale), _p(self.hits), n, st))
+        check(L.ngp_raymarching_train_count(_p(self.rays_o), _p(self.rays_d), _p(self.hits), _p(bits), _p(self.noise),
+                                            m.cascades, m.grid_size, float(m.scale), self.esf, self.max_samples,
+                                            _p(self.counter), _p(self.rays_a), n, st))
+        check(L.ngp_raymarching_train_write(_p(self.rays_o), _p(self.rays_d), _p(self.hits), _p(bits), _p(self.noise),
+                                            m.cascades, m.grid_size, float(m.scale), self.esf, _p(self.counter),
+                                            _p(self.rays_a), _p(self.xyzs), _p(self.dirs), _p(self.deltas), _p(self.ts),
+                                            n, cap, st))
+        nd = _p(self.counter)  # counter[0] = number of valid sample rows, read on the device
+        check(L.ngp_hash_encode_fwd_dyn(_p(self.xyzs), _p(self._table()), C.byref(self._clayout), _p(self.emb), tag,
+                                        cap, nd, self.aabb6, st))
+        check(L.ngp_mlp_fwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.sig), _p(self.rgbs),
+                                cap, nd, st))
+        check(L.ngp_composite_train_fwd(_p(self.sig), _p(self.rgbs), F16, _p(self.deltas), _p(self.ts), _p(self.rays_a),
+                                        self.T_thr, _p(self.total), _p(self.opacity), _p(self.depth), _p(self.rgb),
+                                        _p(self.ws), n, cap, st))
+        self.loss_sum.zero_()
+        bg = 1.0 if self.esf == 0 else 0.0
+        check(L.ngp_mse_loss_grad(_p(self.rgb), _p(self.opacity), _p(self.gt), bg, float(self.tr.loss_scale),
+                                  _p(self.loss_sum), _p(self.g_rgb), _p(self.g_op), n, st))
+        check(L.ngp_composite_train_bwd(_p(self.g_op), _p(self.g_depth), _p(self.g_rgb), None, _p(self.sig),
+                                        _p(self.rgbs), F16, _p(self.deltas), _p(self.ts), _p(self.rays_a), None, None,
+                                        None, self.T_thr, _p(self.dsig), _p(self.drgbs), n, cap, st))
+        fg = self.tr.flat_grad
+        gw = fg[self.P:self.P + 9408]
+        check(L.ngp_mlp_bwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.dsig), _p(self.drgbs),
+                                _p(self.demb), _p(gw), cap, nd, st))
+        check(L.ngp_hash_encode_bwd_dyn(_p(self.xyzs), _p(self.demb), tag, C.byref(self._clayout), _p(fg), cap, nd,
+                                        self.aabb6, st))
+
+    def _enqueue_optimizer(self):
+        L, tr, st = load(), self.tr, self._st()
+        fg = tr.flat_grad
+        tr.found_inf.zero_()
+        check(L.ngp_check_finite(_p(fg), fg.numel(), _p(tr.found_inf), st))
+        inv = parallel.inv_grad_scale(tr.loss_scale, tr.world_size)
+        check(L.ngp_adam_hyper_update(_p(self.step_dev), tr.lr0, tr.lr0 / 30, tr.max_steps, tr.betas[0], tr.betas[1],
+                                      inv, _p(self.hyper), st))
+        enc = self.model.pos_encoder
+        for p, (off, s) in zip(tr.params, tr.slices):
+            shadow = tr._shadow if (tr._shadow is not None and p is enc.hash_table) else None
+            check(L.ngp_adam_step_dyn(_p(p.data), _p(fg[off:off + s]), _p(tr.exp_avg[off:off + s]),
+                                      _p(tr.exp_avg_sq[off:off + s]), _p(shadow), _p(tr.found_inf), _p(self.hyper),
+                                      tr.betas[0], tr.betas[1], tr.eps, 1, s, st))
+
+    def _enqueue(self):
+        self._enqueue_forward_backward()
+        if self.tr.world_size > 1:
+            parallel.allreduce_gradients(self.tr.flat_grad, self.tr.pg)
+        self._enqueue_optimizer()
+
+    def _capture(self):
+        # the graph must not mutate training state while being built: snapshot, warm up + capture, restore
+        tr = self.tr
+        keep = [p.data.clone() for p in tr.params] + [tr.exp_avg.clone(), tr.exp_avg_sq.clone(), self.step_dev.clone()]
+        shadow = None if tr._shadow is None else tr._shadow.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._enqueue()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+        torch.cuda.synchronize()
+        for p, k in zip(tr.params, keep):
+            p.data.copy_(k)
+        tr.exp_avg.copy_(keep[-3])
+        tr.exp_avg_sq.copy_(keep[-2])
+        self.step_dev.copy_(keep[-1])
+        tr.flat_grad.zero_()
+        if shadow is not None:
+            tr._shadow.copy_(shadow)
+
+    # ---------------------------------------------------------------------------------------------
+    def step(self, rays_o, rays_d, rgb_gt, noise=None):
+        """Enqueues one full training step; returns the (device) loss tensor — nothing is synchronised."""
+        self.rays_o.copy_(rays_o, non_blocking=True)
+        self.rays_d.copy_(rays_d, non_blocking=True)
+        self.gt.copy_(rgb_gt, non_blocking=True)
+        if noise is None:
+            self.noise.uniform_()
+        else:
+            self.noise.copy_(noise, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        self.tr.step_count += 1
+        enc = self.model.pos_encoder
+        if self.tr._shadow is not None:
+            enc.adopt_shadow(self.tr._shadow)
+        return self.loss_sum / (3.0 * self.n)
+
+    def stats(self):
+        """(samples marched, rays) of the LAST enqueued step — device tensors, no sync."""
+        return self.counter[0], self.counter[1]
