@@ -164,14 +164,20 @@ def run_ours(args):
                     for b in batches]
 
     sample_counts = []
+    from taichi_nerfs_b200.fast_step import StaticTrainStep
+    fast = None if args.path == "modules" else StaticTrainStep(trainer, BATCH, samples_per_ray_capacity=384)
 
     def one_step(step_idx, b):
         with torch.autocast("cuda", dtype=torch.float16):
             if step_idx % UPDATE_INTERVAL == 0:
                 model.update_density_grid(DENSITY_THRESHOLD, warmup=step_idx < 256)
         rays_o, rays_d = get_rays(b["direction"], b["pose"])
-        loss, results = trainer.step(rays_o, rays_d, b["rgb"])
-        sample_counts.append(results["rm_samples"])
+        if fast is not None:   # the whole step is one CUDA-graph replay, no host sync
+            loss = fast.step(rays_o, rays_d, b["rgb"])
+            sample_counts.append(fast.counter[0].clone())
+        else:                  # reference-shaped module API: render() + autograd + fused Adam
+            loss, results = trainer.step(rays_o, rays_d, b["rgb"])
+            sample_counts.append(results["rm_samples"])
         return loss
 
     def barrier():
@@ -257,7 +263,9 @@ def run_ours(args):
                          "new rays every step" % int(spr * BATCH * 2010 / 1e6),
                    "density_grid_update": f"inside timed loop every {UPDATE_INTERVAL} steps (warm-up mode); "
                                           f"{upd_ms:.3f} ms each",
-                   "mlp": "torch.nn.Linear (cuBLAS) under autocast" if not _fused_mlp() else "fused tcgen05 kernel"},
+                   "mlp": "torch.nn.Linear (cuBLAS) under autocast" if not _fused_mlp() else "fused tcgen05 kernel",
+                   "step_path": "StaticTrainStep: whole step = one CUDA-graph replay, sample count stays on the device"
+                                if fast is not None else "modules API: render() + torch.autograd + fused Adam"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "clocks": clock_info,
@@ -421,6 +429,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-rays", type=int, default=256, help="rays per step of the reference arm's bounded sample")
+    ap.add_argument("--path", default="graph", choices=["graph", "modules"],
+                    help="graph: StaticTrainStep (one CUDA graph per step, sync-free); "
+                         "modules: render()+autograd through the reference-shaped module API")
     ap.add_argument("--ncu-window", type=int, default=0,
                     help="profiling aid: wrap this many extra steps in cudaProfilerStart/Stop "
                          "(use with `ncu --profile-from-start off`); numbers printed under ncu are not bench values")
