@@ -219,9 +219,12 @@ def run_ours(args):
     for s in range(args.warmup):
         one_step(s, batches[s])
     launches0 = _lib.launch_count()
+    replays0 = fast.replays if fast is not None else 0
     ms_total = timed(lambda: [one_step(args.warmup + k, batches[args.warmup + k]) for k in range(args.steps)])
     clock_info = clocks.stop() if rank == 0 else None
-    launches = _lib.launch_count() - launches0
+    launches = _lib.launch_count() - launches0   # eager launches of libngp_b200 kernels
+    if fast is not None:                          # + kernel nodes executed by CUDA-graph replays
+        launches += (fast.replays - replays0) * fast.kernels_per_replay
     ms_step = ms_total / args.steps
     value = world * BATCH / (ms_step * 1e-3)
     spr = float(torch.stack([c.float() for c in sample_counts[-args.steps:]]).mean()) / BATCH

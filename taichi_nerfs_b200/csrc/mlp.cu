@@ -212,6 +212,44 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, uint8_t* dst,
     }
 }
 
+// per-thread inputs of one tile row, fetched one tile ahead so the ~1 us DRAM latency overlaps the
+// previous tile's MMA / epilogue rounds
+struct RowIn {
+    uint4 e[4];          // 32 fp16 embedding values
+    float dx, dy, dz;
+    float dsig, dr[3];   // backward only
+};
+template <typename TEmb, bool kBwd>
+__device__ __forceinline__ RowIn load_row(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
+                                           const float* __restrict__ dsigmas, const __half* __restrict__ drgbs,
+                                           int64_t i, bool valid) {
+    RowIn r;
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) r.e[kc] = make_uint4(0, 0, 0, 0);
+    r.dx = 0.f; r.dy = 0.f; r.dz = 1.f; r.dsig = 0.f; r.dr[0] = r.dr[1] = r.dr[2] = 0.f;
+    if (valid) {
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            if constexpr (sizeof(TEmb) == 2) {
+                r.e[kc] = __ldg(reinterpret_cast<const uint4*>(emb + i * 32) + kc);
+            } else {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8 + 4));
+                r.e[kc] = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
+            }
+        }
+        r.dx = __ldg(dirs + i * 3 + 0);
+        r.dy = __ldg(dirs + i * 3 + 1);
+        r.dz = __ldg(dirs + i * 3 + 2);
+        if constexpr (kBwd) {
+            r.dsig = __ldg(dsigmas + i);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) r.dr[c] = __half2float(drgbs[i * 3 + c]);
+        }
+    }
+    return r;
+}
+
 template <typename TEmb>
 __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
                                                            ngp_mlp_weights w, float* __restrict__ sigmas,
@@ -247,30 +285,19 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restric
                    aW4 = smem_u32(smem + kW4), aW5 = smem_u32(smem + kW5);
 
     const int64_t n_tiles = (n + kTile - 1) / kTile;
+    RowIn cur = load_row<TEmb, false>(emb, dirs, nullptr, nullptr, (int64_t)blockIdx.x * kTile + tid,
+                                      (int64_t)blockIdx.x * kTile + tid < n);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * kTile + tid;
         const bool valid = i < n;
 
-        // ---- stage X = emb[i, 0:32] as fp16 into bufA (K = 32 layout)
+        // ---- stage X = emb[i, 0:32] as fp16 into bufA (K = 32 layout); inputs were fetched one tile ago
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (valid) {
-                if constexpr (sizeof(TEmb) == 2) {
-                    v = __ldg(reinterpret_cast<const uint4*>(emb + i * 32) + kc);
-                } else {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8 + 4));
-                    v = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
-                }
-            }
-            *reinterpret_cast<uint4*>(smem + kBufA + chunk_off(tid, kc, 32)) = v;
-        }
-        float dx = 0.f, dy = 0.f, dz = 1.f;
-        if (valid) {
-            dx = dirs[i * 3 + 0];
-            dy = dirs[i * 3 + 1];
-            dz = dirs[i * 3 + 2];
+        for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(smem + kBufA + chunk_off(tid, kc, 32)) = cur.e[kc];
+        const float dx = cur.dx, dy = cur.dy, dz = cur.dz;
+        {   // prefetch the next tile of this CTA
+            const int64_t in = (tile + gridDim.x) * kTile + tid;
+            cur = load_row<TEmb, false>(emb, dirs, nullptr, nullptr, in, in < n);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -491,33 +518,20 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
 
     bool first = true;  // first tile of this CTA: weight-gradient accumulators start from zero
     const int64_t n_tiles = (n + kTile - 1) / kTile;
+    RowIn cur = load_row<TEmb, true>(emb, dirs, dsigmas, drgbs, (int64_t)blockIdx.x * kTile + tid,
+                                     (int64_t)blockIdx.x * kTile + tid < n);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * kTile + tid;
         const bool valid = i < n;
 
         // ================= forward recompute =================
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (valid) {
-                if constexpr (sizeof(TEmb) == 2) {
-                    v = __ldg(reinterpret_cast<const uint4*>(emb + i * 32) + kc);
-                } else {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8 + 4));
-                    v = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
-                }
-            }
-            *reinterpret_cast<uint4*>(smem + kE + chunk_off(tid, kc, 32)) = v;
-        }
-        float dx = 0.f, dy = 0.f, dz = 1.f, dsig = 0.f, dr[3] = {0.f, 0.f, 0.f};
-        if (valid) {
-            dx = dirs[i * 3 + 0];
-            dy = dirs[i * 3 + 1];
-            dz = dirs[i * 3 + 2];
-            dsig = dsigmas[i];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) dr[c] = __half2float(drgbs[i * 3 + c]);
+        for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(smem + kE + chunk_off(tid, kc, 32)) = cur.e[kc];
+        const float dx = cur.dx, dy = cur.dy, dz = cur.dz, dsig = cur.dsig;
+        const float dr[3] = {cur.dr[0], cur.dr[1], cur.dr[2]};
+        {   // prefetch the next tile of this CTA (consumed one iteration later)
+            const int64_t in = (tile + gridDim.x) * kTile + tid;
+            cur = load_row<TEmb, true>(emb, dirs, dsigmas, drgbs, in, in < n);
         }
         NGP_ROUND(issue_layer_mma(tmem_base, aE, aW1, 32, 64))          // H1 = relu(E W1^T)
         epilogue_hidden(tmem_row, smem + kH1, tid);

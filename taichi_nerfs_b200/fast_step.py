@@ -74,6 +74,8 @@ class StaticTrainStep:
         jitter = (torch.arange(self.n, device=dev, dtype=f32)[:, None] % 97) * 1e-3
         self.rays_d[:] = -self.rays_o + jitter * torch.tensor([0.3, -0.2, 0.1], device=dev)
         self.graph = None
+        self.kernels_per_replay = 0
+        self.replays = 0
         self.use_graph = use_graph and parallel.world_info(trainer.pg)[1] == 1
         if self.use_graph:
             self._capture()
@@ -153,8 +155,10 @@ class StaticTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self._enqueue()
+        self.kernels_per_replay = _lib.launch_count() - before  # libngp_b200 kernel nodes in the graph
         torch.cuda.synchronize()
         for p, k in zip(tr.params, keep):
             p.data.copy_(k)
@@ -177,6 +181,7 @@ class StaticTrainStep:
             self.noise.copy_(noise, non_blocking=True)
         if self.graph is not None:
             self.graph.replay()
+            self.replays += 1
         else:
             self._enqueue()
         self.tr.step_count += 1
