@@ -153,3 +153,44 @@ def test_static_step_capacity_overflow_is_safe(lego_bitfield):
     assert torch.isfinite(loss).all()
     assert 0 < int(fs.counter[0]) <= fs.cap
     assert all(torch.isfinite(p).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(name="lego_fp32", scale=0.5, half=False, esf=0.0),          # BASELINE configs[0]: fp32 encoder
+    dict(name="garden_half", scale=16.0, half=True, esf=1 / 256),    # BASELINE configs[2]: 6 cascades, 4096 layout
+])
+def test_static_step_other_configs(cfg, monkeypatch):
+    """fp32-encoder and multi-cascade (garden-scale) configurations: graph step == module/autograd step."""
+    from modules.networks import NGP
+    from oracle.train_step import make_rays
+    from taichi_nerfs_b200.fast_step import StaticTrainStep
+    from taichi_nerfs_b200.trainer import NGPTrainer
+
+    def build():
+        torch.manual_seed(4)
+        m = NGP(scale=cfg["scale"], max_res=1024 if cfg["scale"] == 0.5 else 4096, half_opt=cfg["half"]).cuda()
+        with torch.no_grad():
+            if cfg["half"]:
+                m.pos_encoder.hash_table.mul_(2e3)
+            g = torch.Generator(device='cuda').manual_seed(5)
+            m.density_bitfield.copy_((torch.rand(m.density_bitfield.shape, device='cuda', generator=g) < 0.3) *
+                                     torch.randint(1, 256, m.density_bitfield.shape, device='cuda', generator=g).to(torch.uint8))
+        return m, NGPTrainer(m, lr=1e-2)
+
+    n = 1024
+    o, d = make_rays(n, seed=12, radius=1.4 if cfg["scale"] == 0.5 else 3.0)
+    o, d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    gt, noise = torch.rand(n, 3, device='cuda'), torch.rand(n, device='cuda')
+    m1, t1 = build()
+    assert m1.cascades == (1 if cfg["scale"] == 0.5 else 6)
+    monkeypatch.setattr(torch, 'rand_like', lambda t, **k: noise.clone())
+    l1 = [float(t1.step(o, d, gt, cfg["esf"])[0].detach()) for _ in range(2)]
+    monkeypatch.undo()
+    m2, t2 = build()
+    fs = StaticTrainStep(t2, n, samples_per_ray_capacity=512, exp_step_factor=cfg["esf"], use_graph=True)
+    l2 = [float(fs.step(o, d, gt, noise=noise)) for _ in range(2)]
+    assert int(fs.counter[0]) > 1000
+    for a, b in zip(l1, l2):
+        assert abs(a - b) < 3e-3 * max(a, 1e-6), (l1, l2)
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert float(((p1 - p2).abs() > 2e-3).float().mean()) < 5e-3
