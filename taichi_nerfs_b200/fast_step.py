@@ -76,9 +76,17 @@ class StaticTrainStep:
         self.graph = None
         self.kernels_per_replay = 0
         self.replays = 0
-        self.use_graph = use_graph and parallel.world_info(trainer.pg)[1] == 1
+        self.use_graph = bool(use_graph)
         if self.use_graph:
-            self._capture()
+            try:
+                self._capture()  # with world_size > 1 the NCCL all-reduce is captured as a graph node too
+            except RuntimeError as e:  # pragma: no cover - depends on the NCCL / driver combination
+                if parallel.world_info(trainer.pg)[1] == 1:
+                    raise
+                print(f"[StaticTrainStep] CUDA-graph capture with NCCL failed ({e}); falling back to eager enqueue")
+                self.graph = None
+                self.use_graph = False
+                torch.cuda.synchronize()
 
     # ---------------------------------------------------------------------------------------------
     def _st(self):
