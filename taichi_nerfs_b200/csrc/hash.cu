@@ -26,8 +26,9 @@ constexpr int kTile = 512;
 constexpr int kChunk = 16;
 constexpr int kThreads = 512;
 constexpr int kRow = kTile + kTile / kChunk + 1;  // 545 words: chunk stride 17 (conflict-free), odd row stride
-constexpr int kXChunk = kChunk * 3 + 1;           // xyz staging: 49 words per 16-sample chunk -> lanes hit distinct banks
-constexpr int kXWords = (kTile / kChunk) * kXChunk;
+constexpr int kXChunk = kChunk + 1;               // xyz staged as float4, 17 float4 (272 B) per 16-sample chunk:
+                                                  // one LDS.128 per sample, conflict-free per quarter warp
+constexpr int kXWords = (kTile / kChunk) * kXChunk * 4;
 
 // optional run-time extras: device-side row count and the world->[0,1] normalisation of NGP.density
 struct Dyn {
@@ -155,10 +156,14 @@ __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restr
     const int64_t base = (int64_t)blockIdx.x * kTile;
     if (base >= n) return;
     const int rows = (int)min((int64_t)kTile, n - base);
-    for (int k = threadIdx.x; k < rows * 3; k += kThreads) {
-        float v = xyz[base * 3 + k];
-        if (dyn.normalize) v = f_div(f_sub(v, dyn.lo[k % 3]), dyn.span[k % 3]);  // networks.py:144
-        sx[k + k / (kChunk * 3)] = v;
+    for (int r = threadIdx.x; r < rows; r += kThreads) {
+        float v[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[k] = xyz[(base + r) * 3 + k];
+            if (dyn.normalize) v[k] = f_div(f_sub(v[k], dyn.lo[k]), dyn.span[k]);  // networks.py:144
+        }
+        reinterpret_cast<float4*>(sx)[r + r / kChunk] = make_float4(v[0], v[1], v[2], 0.0f);
     }
     __syncthreads();
 
@@ -174,8 +179,8 @@ __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restr
         for (int j = 0; j < kChunk; ++j) {
             const int s = lane * kChunk + j;
             if (s >= rows) break;
-            const float* xp = sx + lane * kXChunk + j * 3;
-            const float x[3] = {xp[0], xp[1], xp[2]};
+            const float4 xv = reinterpret_cast<const float4*>(sx)[lane * kXChunk + j];
+            const float x[3] = {xv.x, xv.y, xv.z};
             uint32_t g[3];
             float pos[3];
             grid_pos<kHalf>(x, m, g, pos);
@@ -227,9 +232,21 @@ __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restr
     __syncthreads();
     // coalesced write-out of the [rows, L] result
     V2* o2 = reinterpret_cast<V2*>(out) + base * L;
-    for (int k = threadIdx.x; k < rows * L; k += kThreads) {
-        const int r = k / L, l = k - r * L;
-        o2[k] = tile[l * kRow + r + r / kChunk];
+    constexpr int kVec = 16 / sizeof(V2);  // entries per 16-byte store (4 for fp16, 2 for fp32)
+    if (L % kVec == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const int groups = L / kVec;
+        for (int k = threadIdx.x; k < rows * groups; k += kThreads) {
+            const int r = k / groups, l0 = (k - r * groups) * kVec;
+            V2 v[kVec];
+#pragma unroll
+            for (int q = 0; q < kVec; ++q) v[q] = tile[(l0 + q) * kRow + r + r / kChunk];
+            *reinterpret_cast<uint4*>(o2 + (int64_t)r * L + l0) = *reinterpret_cast<const uint4*>(v);
+        }
+    } else {
+        for (int k = threadIdx.x; k < rows * L; k += kThreads) {
+            const int r = k / L, l = k - r * L;
+            o2[k] = tile[l * kRow + r + r / kChunk];
+        }
     }
 }
 
@@ -254,15 +271,31 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
     const int64_t base = (int64_t)blockIdx.x * kTile;
     if (base >= n) return;
     const int rows = (int)min((int64_t)kTile, n - base);
-    for (int k = threadIdx.x; k < rows * 3; k += kThreads) {
-        float v = xyz[base * 3 + k];
-        if (dyn.normalize) v = f_div(f_sub(v, dyn.lo[k % 3]), dyn.span[k % 3]);  // networks.py:144
-        sx[k + k / (kChunk * 3)] = v;
+    for (int r = threadIdx.x; r < rows; r += kThreads) {
+        float v[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[k] = xyz[(base + r) * 3 + k];
+            if (dyn.normalize) v[k] = f_div(f_sub(v[k], dyn.lo[k]), dyn.span[k]);  // networks.py:144
+        }
+        reinterpret_cast<float4*>(sx)[r + r / kChunk] = make_float4(v[0], v[1], v[2], 0.0f);
     }
     const V2* d2 = reinterpret_cast<const V2*>(dout) + base * L;
-    for (int k = threadIdx.x; k < rows * L; k += kThreads) {
-        const int r = k / L, l = k - r * L;
-        tile[l * kRow + r + r / kChunk] = d2[k];
+    constexpr int kVec = 16 / sizeof(V2);
+    if (L % kVec == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0) {
+        const int groups = L / kVec;
+        for (int k = threadIdx.x; k < rows * groups; k += kThreads) {
+            const int r = k / groups, l0 = (k - r * groups) * kVec;
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(d2 + (int64_t)r * L + l0));
+            const V2* v = reinterpret_cast<const V2*>(&raw);
+#pragma unroll
+            for (int q = 0; q < kVec; ++q) tile[(l0 + q) * kRow + r + r / kChunk] = v[q];
+        }
+    } else {
+        for (int k = threadIdx.x; k < rows * L; k += kThreads) {
+            const int r = k / L, l = k - r * L;
+            tile[l * kRow + r + r / kChunk] = d2[k];
+        }
     }
     __syncthreads();
 
@@ -297,8 +330,8 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
         if constexpr (kHalf) dy = __half22float2(trow[j]);
         else dy = trow[j];
         if (dy.x == 0.0f && dy.y == 0.0f) continue;  // hash_encoder_half.py:210
-        const float* xp = sx + lane * kXChunk + j * 3;
-        const float x[3] = {xp[0], xp[1], xp[2]};
+        const float4 xv = reinterpret_cast<const float4*>(sx)[lane * kXChunk + j];
+        const float x[3] = {xv.x, xv.y, xv.z};
         uint32_t g[3];
         float pos[3];
         grid_pos<kHalf>(x, m, g, pos);
