@@ -12,7 +12,8 @@
  * container, so per-kernel parity is "unpinned by the reference".  What is
  * pinned: the hash layout constants printed in notebooks/pipeline.ipynb
  * (tests/test_layout.py) and an end-to-end render of the reference's shipped,
- * trained Lego deployment model through this oracle (oracle/kat_lego.py).
+ * trained Lego deployment model through this oracle (oracle/kat_lego.py ->
+ * tests/golden/lego_kat.png: the yellow bulldozer comes out; tests/test_kat_lego.py).
  *
  * Every function cites the reference file:line it follows.  Build:
  *   gcc -O2 -march=x86-64-v3 -ffp-contract=off -fopenmp -shared -fPIC
