@@ -355,6 +355,83 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
     if (pending) flush();
 }
 
+// ---- generic feature width (F = 1..8, e.g. the reference's --deployment config L=4 F=4) -----------
+// Plain thread-per-(sample, level) kernels; the tuned kernels above cover the stock F = 2.
+template <typename T>
+__global__ void __launch_bounds__(256) hash_fwd_generic_kernel(const float* __restrict__ xyz, const T* __restrict__ table,
+                                                               const __grid_constant__ ngp_hash_layout lay,
+                                                               T* __restrict__ out, int64_t n_max, const Dyn dyn) {
+    constexpr bool kHalf = sizeof(T) == 2;
+    const int64_t n = effective_n(dyn, n_max);
+    const int L = lay.n_levels, F = lay.feat_dim;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n * L) return;
+    const int64_t i = gid / L;
+    const int level = (int)(gid - i * L);
+    float x[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        x[k] = xyz[i * 3 + k];
+        if (dyn.normalize) x[k] = f_div(f_sub(x[k], dyn.lo[k]), dyn.span[k]);
+    }
+    const LevelMeta m = level_meta(lay, level);
+    uint32_t g[3], idx[8];
+    float pos[3], w[8];
+    grid_pos<kHalf>(x, m, g, pos);
+    corner_indices(m, g, idx);
+    corner_weights(pos, w);
+    for (int f = 0; f < F; ++f) {
+        if constexpr (kHalf) {
+            __half acc = __float2half_rn(0.0f);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                acc = __hadd(acc, __float2half_rn(f_mul(w[c], __half2float(table[(int64_t)idx[c] * F + f]))));
+            out[i * L * F + level * F + f] = acc;
+        } else {
+            float acc = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc = f_add(acc, f_mul(w[c], table[(int64_t)idx[c] * F + f]));
+            out[i * L * F + level * F + f] = acc;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) hash_bwd_generic_kernel(const float* __restrict__ xyz, const T* __restrict__ dout,
+                                                               const __grid_constant__ ngp_hash_layout lay,
+                                                               float* __restrict__ grad_table, int64_t n_max,
+                                                               const Dyn dyn) {
+    constexpr bool kHalf = sizeof(T) == 2;
+    const int64_t n = effective_n(dyn, n_max);
+    const int L = lay.n_levels, F = lay.feat_dim;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n * L) return;
+    const int64_t i = gid / L;
+    const int level = (int)(gid - i * L);
+    float dy[8];
+    bool any = false;
+    for (int f = 0; f < F; ++f) {
+        dy[f] = load_as_float(dout, i * L * F + level * F + f);
+        any |= dy[f] != 0.0f;
+    }
+    if (!any) return;
+    float x[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        x[k] = xyz[i * 3 + k];
+        if (dyn.normalize) x[k] = f_div(f_sub(x[k], dyn.lo[k]), dyn.span[k]);
+    }
+    const LevelMeta m = level_meta(lay, level);
+    uint32_t g[3], idx[8];
+    float pos[3], w[8];
+    grid_pos<kHalf>(x, m, g, pos);
+    corner_indices(m, g, idx);
+    corner_weights(pos, w);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        for (int f = 0; f < F; ++f) atomicAdd(grad_table + (int64_t)idx[c] * F + f, w[c] * dy[f]);
+}
+
 __device__ __forceinline__ uint32_t corner_index(const LevelMeta& m, const uint32_t g[3], int c) {
     uint32_t idx[8];
     corner_indices(m, g, idx);
@@ -436,7 +513,7 @@ Dyn make_dyn(const int32_t* n_dev, const float* aabb6) {
 int check_layout(const ngp_hash_layout* lay) {
     NGP_REQUIRE(lay != nullptr, "null layout");
     NGP_REQUIRE(lay->n_levels >= 1 && lay->n_levels <= NGP_MAX_LEVELS, "n_levels out of range");
-    NGP_REQUIRE(lay->feat_dim == 2, "CUDA path supports feature_per_level == 2 only");
+    NGP_REQUIRE(lay->feat_dim >= 1 && lay->feat_dim <= 8, "feature_per_level must be in [1, 8]");
     return 0;
 }
 
@@ -457,8 +534,17 @@ int ngp_hash_encode_fwd_dyn(const float* xyz, const void* table, const ngp_hash_
     NGP_REQUIRE(dtype == NGP_F32 || dtype == NGP_F16, "bad dtype");
     if (n == 0) return 0;
     NGP_REQUIRE(xyz && table && out, "null pointer");
-    const unsigned grid = (unsigned)((n + kTile - 1) / kTile);
     cudaStream_t st = ngp::as_stream(stream);
+    if (layout->feat_dim != 2) {  // generic feature width
+        const unsigned gg = (unsigned)((n * layout->n_levels + 255) / 256);
+        if (dtype == NGP_F16)
+            hash_fwd_generic_kernel<__half><<<gg, 256, 0, st>>>(xyz, (const __half*)table, *layout, (__half*)out, n, dyn);
+        else
+            hash_fwd_generic_kernel<float><<<gg, 256, 0, st>>>(xyz, (const float*)table, *layout, (float*)out, n, dyn);
+        NGP_LAUNCHED("hash_fwd_generic_kernel");
+        return 0;
+    }
+    const unsigned grid = (unsigned)((n + kTile - 1) / kTile);
     if (int rc = configure_smem()) return rc;
     if (dtype == NGP_F16)
         hash_fwd_kernel<__half><<<grid, kThreads, smem_bytes(layout->n_levels, 4), st>>>(xyz, (const __half*)table, *layout, (__half*)out, n, dyn);
@@ -482,8 +568,17 @@ int ngp_hash_encode_bwd_dyn(const float* xyz, const void* dout, int dout_dtype, 
     if (n == 0) return 0;
     NGP_REQUIRE(xyz && dout && grad_table, "null pointer");
     NGP_REQUIRE((reinterpret_cast<uintptr_t>(grad_table) & 7) == 0, "grad_table must be 8-byte aligned");
-    const unsigned grid = (unsigned)((n + kTile - 1) / kTile);
     cudaStream_t st = ngp::as_stream(stream);
+    if (layout->feat_dim != 2) {
+        const unsigned gg = (unsigned)((n * layout->n_levels + 255) / 256);
+        if (dout_dtype == NGP_F16)
+            hash_bwd_generic_kernel<__half><<<gg, 256, 0, st>>>(xyz, (const __half*)dout, *layout, grad_table, n, dyn);
+        else
+            hash_bwd_generic_kernel<float><<<gg, 256, 0, st>>>(xyz, (const float*)dout, *layout, grad_table, n, dyn);
+        NGP_LAUNCHED("hash_bwd_generic_kernel");
+        return 0;
+    }
+    const unsigned grid = (unsigned)((n + kTile - 1) / kTile);
     if (int rc = configure_smem()) return rc;
     if (dout_dtype == NGP_F16)
         hash_bwd_kernel<__half><<<grid, kThreads, smem_bytes(layout->n_levels, 4), st>>>(xyz, (const __half*)dout, *layout, grad_table, n, dyn);
@@ -500,6 +595,7 @@ int ngp_hash_encode_bwd_input(const float* xyz, const void* table, const void* d
     NGP_REQUIRE(dtype == NGP_F32 || dtype == NGP_F16, "bad dtype");
     if (n == 0) return 0;
     NGP_REQUIRE(xyz && table && dout && dx, "null pointer");
+    NGP_REQUIRE(layout->feat_dim == 2, "dL/dx is implemented for feature_per_level == 2");
     const unsigned grid = (unsigned)((n + 255) / 256);
     cudaStream_t st = ngp::as_stream(stream);
     if (dtype == NGP_F16)

@@ -50,7 +50,7 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.ngp_hash_encode_fwd(None, None, C.byref(lay), None, 7, 8, None) < 0
     assert b"dtype" in lib.ngp_last_error()
     bad = make_hash_layout(2 ** 19, 16, 16, 1024, 2).as_ctypes()
-    bad.feat_dim = 3
+    bad.feat_dim = 9
     assert lib.ngp_hash_encode_fwd(None, None, C.byref(bad), None, 0, 8, None) < 0
     assert lib.ngp_adam_step(None, None, None, None, None, None, 1e-2, 0.9, 0.999, 1e-15, 1.0, 0, 0, 8, None) < 0
     # empty inputs are a no-op success

@@ -427,3 +427,38 @@ def test_packbits_device_threshold(ops, oracle):
         eff = min(mean, thr)  # python semantics of networks.py:288-290 (NaN mean -> NaN threshold -> no bits)
         want = oracle.packbits(grid, eff) if eff == eff else np.zeros(128 ** 3 // 8, np.uint8)
         assert np.array_equal(N(bits), want)
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_hash_generic_feature_width(ops, oracle, half):
+    """--deployment configuration of the reference (train.py:88-99): L=4, F=4, 32->128, T=2^21, all dense."""
+    rng = np.random.default_rng(38)
+    lay = make_hash_layout(2 ** 21, 4, 32, 128, 4)
+    n = 3000
+    xyz = rng.random((n, 3), dtype=np.float32)
+    table = rng.standard_normal(lay.total_param_size).astype(np.float16 if half else np.float32)
+    ref = oracle.hash_encode_fwd(xyz, table, lay)
+    got = N(ops.hash_encode_fwd(T(xyz), T(table), lay.as_ctypes(), lay.out_dim))
+    assert np.array_equal(got.view(np.uint8), ref.view(np.uint8))
+    dout = rng.standard_normal((n, lay.out_dim)).astype(table.dtype)
+    gref = oracle.hash_encode_bwd(xyz, dout, lay)
+    g = torch.zeros(lay.total_param_size, device=DEV)
+    ops.hash_encode_bwd(T(xyz), T(dout), lay.as_ctypes(), g)
+    np.testing.assert_allclose(N(g), gref, rtol=1e-3, atol=1e-4)
+
+
+def test_deployment_model_config_trains():
+    """NGP(**deployment config) falls back to nn.Linear MLPs + generic-F hash kernels and can take a step."""
+    from modules.networks import NGP
+    from taichi_nerfs_b200.trainer import NGPTrainer
+    from oracle.train_step import make_rays
+    m = NGP(scale=0.5, levels=4, feature_per_level=4, base_res=32, max_res=128, log2_T=21, xyz_net_width=16,
+            rgb_net_width=16, rgb_net_depth=1).cuda()
+    assert not m._fusable(next(m.parameters()))
+    with torch.no_grad():
+        m.density_bitfield.fill_(255)
+    o, d = make_rays(512, seed=13)
+    tr = NGPTrainer(m)
+    before = m.pos_encoder.hash_table.detach().clone()
+    loss, res = tr.step(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), torch.rand(512, 3, device='cuda'))
+    assert torch.isfinite(loss) and (m.pos_encoder.hash_table != before).any()
