@@ -203,17 +203,23 @@ __device__ __forceinline__ CellTest test_cell(const MarchParams& p, const Ray& r
 
 constexpr int kRaysPerBlock = 4;
 
-template <bool kWrite>
+// kMode: 0 = count (pass 1), 1 = write (pass 2), 2 = single pass for test-time frames (sample times are
+// buffered in shared memory, the ray reserves its rows with one atomicAdd, then writes them coalesced)
+constexpr int kMaxFrameSamples = 1024;
+template <int kMode>
 __global__ void __launch_bounds__(kRaysPerBlock * 32)
 march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                         const float* __restrict__ hits_t, const float* __restrict__ noise, MarchParams p,
                         int max_samples, int32_t* __restrict__ rays_a, int32_t* __restrict__ counter,
                         float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
                         float* __restrict__ ts, int64_t n, int64_t capacity) {
+    constexpr bool kWrite = kMode == 1;
+    __shared__ float sbuf[kMode == 2 ? kRaysPerBlock * kMaxFrameSamples : 1];
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
     if (r >= n) return;
     const unsigned full = 0xffffffffu;
+    float* my_buf = sbuf + (kMode == 2 ? (threadIdx.x >> 5) * kMaxFrameSamples : 0);
 
     int limit = max_samples;
     int64_t start = 0;
@@ -232,7 +238,8 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
     Ray ray;
     load_ray(rays_o, rays_d, r, ray);
     const float t2 = hits_t[r * 2 + 1];
-    float t = train_t0(hits_t, noise, r, p);
+    float t = kMode == 2 ? hits_t[r * 2 + 0] : train_t0(hits_t, noise, r, p);  // test time: no jitter
+    if (kMode == 2 && !(0.0f < t)) t = -1.0f;                                   // ray_march.py:226 (strict 0 < t)
     int emitted = 0;
     float skip_until = -INFINITY;
     const bool const_dt = p.esf == 0.0f;
@@ -318,13 +325,40 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
             ts[i] = my_t;
             deltas[i] = c.dt;
         }
+        if (kMode == 2 && ((emit >> lane) & 1u)) my_buf[emitted + __popc(emit & ((1u << lane) - 1u))] = my_t;
         emitted += __popc(emit);
         if (valid_mask != full) break;  // the ray left the box inside this chunk
         t = tk;
     }
-    if (!kWrite && lane == 0) {
+    if (kMode == 0 && lane == 0) {
         rays_a[r * 3 + 0] = (int32_t)r;
         rays_a[r * 3 + 2] = emitted;
+    }
+    if (kMode == 2) {
+        int s0 = 0;
+        if (lane == 0 && emitted > 0) s0 = atomicAdd(&counter[0], emitted);  // reserve a contiguous row range
+        s0 = __shfl_sync(full, s0, 0);
+        const bool fits = (int64_t)s0 + emitted <= capacity;
+        if (lane == 0) {
+            rays_a[r * 3 + 0] = (int32_t)r;
+            rays_a[r * 3 + 1] = fits ? s0 : 0;
+            rays_a[r * 3 + 2] = fits ? emitted : 0;
+            if (!fits) atomicAdd(&counter[1], 1);  // number of rays dropped for lack of capacity
+        }
+        if (!fits) return;
+        __syncwarp();
+        for (int k = lane; k < emitted; k += 32) {
+            const float tt = my_buf[k];
+            const int64_t i = (int64_t)s0 + k;
+            xyzs[i * 3 + 0] = f_add(ray.o[0], f_mul(tt, ray.d[0]));
+            xyzs[i * 3 + 1] = f_add(ray.o[1], f_mul(tt, ray.d[1]));
+            xyzs[i * 3 + 2] = f_add(ray.o[2], f_mul(tt, ray.d[2]));
+            dirs[i * 3 + 0] = ray.d[0];
+            dirs[i * 3 + 1] = ray.d[1];
+            dirs[i * 3 + 2] = ray.d[2];
+            ts[i] = tt;
+            deltas[i] = calc_dt(tt, p.esf, p.dt_max);
+        }
     }
 }
 
@@ -450,7 +484,7 @@ int ngp_raymarching_train_count(const float* rays_o, const float* rays_d, const 
     const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
     if (n_rays > 0) {
         const unsigned grid = (unsigned)((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
-        march_train_warp_kernel<false><<<grid, kRaysPerBlock * 32, 0, st>>>(
+        march_train_warp_kernel<0><<<grid, kRaysPerBlock * 32, 0, st>>>(
             rays_o, rays_d, hits_t, noise, p, max_samples, rays_a, counter, nullptr, nullptr, nullptr, nullptr,
             n_rays, 0);
         NGP_LAUNCHED("march_train_warp_kernel<count>");
@@ -471,9 +505,26 @@ int ngp_raymarching_train_write(const float* rays_o, const float* rays_d, const 
     NGP_REQUIRE(capacity == 0 || (xyzs && dirs && deltas && ts), "null output");
     const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
     const unsigned grid = (unsigned)((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
-    march_train_warp_kernel<true><<<grid, kRaysPerBlock * 32, 0, ngp::as_stream(stream)>>>(
+    march_train_warp_kernel<1><<<grid, kRaysPerBlock * 32, 0, ngp::as_stream(stream)>>>(
         rays_o, rays_d, hits_t, noise, p, 0, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity);
     NGP_LAUNCHED("march_train_warp_kernel<write>");
+    return 0;
+}
+
+int ngp_raymarching_frame(const float* rays_o, const float* rays_d, const float* hits_t,
+                          const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                          float exp_step_factor, int max_samples, int32_t* counter, int32_t* rays_a, float* xyzs,
+                          float* dirs, float* deltas, float* ts, int64_t n_rays, int64_t capacity, void* stream) {
+    NGP_REQUIRE(n_rays >= 0 && capacity >= 0, "negative size");
+    if (n_rays == 0) return 0;
+    NGP_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && counter && rays_a, "null pointer");
+    NGP_REQUIRE(capacity == 0 || (xyzs && dirs && deltas && ts), "null output");
+    NGP_REQUIRE(max_samples >= 1 && max_samples <= kMaxFrameSamples, "max_samples must be in [1, 1024]");
+    const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
+    const unsigned grid = (unsigned)((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
+    march_train_warp_kernel<2><<<grid, kRaysPerBlock * 32, 0, ngp::as_stream(stream)>>>(
+        rays_o, rays_d, hits_t, nullptr, p, max_samples, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity);
+    NGP_LAUNCHED("march_train_warp_kernel<frame>");
     return 0;
 }
 

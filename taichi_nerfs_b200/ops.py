@@ -78,6 +78,16 @@ def raymarching_train_write(rays_o, rays_d, hits_t, bitfield, noise, cascades, s
           "raymarching_train_write")
 
 
+def raymarching_frame(rays_o, rays_d, hits_t, bitfield, cascades, scale, exp_step_factor, grid_size, max_samples,
+                      counter, rays_a, xyzs, dirs, deltas, ts):
+    """Single-pass test-time march into capacity buffers; counter = [rows reserved, rays dropped]."""
+    n, cap = rays_o.shape[0], deltas.shape[0]
+    check(load().ngp_raymarching_frame(_ptr(rays_o), _ptr(rays_d), _ptr(hits_t), _ptr(bitfield), int(cascades),
+                                       int(grid_size), float(scale), float(exp_step_factor), int(max_samples),
+                                       _ptr(counter), _ptr(rays_a), _ptr(xyzs), _ptr(dirs), _ptr(deltas), _ptr(ts),
+                                       n, cap, _stream()), "raymarching_frame")
+
+
 # ---- a3 ------------------------------------------------------------------------------------------
 def raymarching_test(rays_o, rays_d, hits_t, alive_indices, bitfield, cascades, scale, exp_step_factor, grid_size,
                      max_samples, ray_indices, valid_mask, deltas, ts, samples_counter):

@@ -37,26 +37,49 @@ def render_frame(model, rays_o, rays_d, exp_step_factor=0.0, T_threshold=1e-4, m
     lo, span = model.xyz_min, (model.xyz_max - model.xyz_min)
     total = 0
     zeros = torch.zeros(min(block_rays, n), device=dev, dtype=torch.float32)  # test-time march has no jitter
+    caps = model.__dict__.setdefault('_frame_capacity', {})  # learned per ray block from the previous frame
     for b in range(0, n, block_rays):
         e = min(b + block_rays, n)
         o, d = rays_o[b:e], rays_d[b:e]
         hits = ops.ray_aabb_intersect(o, d, model.scale)
-        noise = zeros[: e - b]
-        counter, rays_a = ops.raymarching_train_count(o, d, hits, model.density_bitfield, noise, model.cascades,
-                                                      model.scale, exp_step_factor, model.grid_size, max_samples)
-        S = int(counter[0].item())  # one host read per ray block (the loop needs >= 3 per iteration)
+        key = (b, e - b)
+        done = False
+        if key in caps and max_samples <= 1024:
+            # single-pass march: each ray reserves its rows with one atomic; capacity from the last frame
+            cap = caps[key]
+            counter = torch.zeros(2, device=dev, dtype=torch.int32)
+            rays_a = torch.empty(e - b, 3, device=dev, dtype=torch.int32)
+            xyzs = torch.empty(cap, 3, device=dev, dtype=torch.float32)
+            dirs = torch.empty(cap, 3, device=dev, dtype=torch.float32)
+            deltas = torch.empty(cap, device=dev, dtype=torch.float32)
+            ts = torch.empty(cap, device=dev, dtype=torch.float32)
+            ops.raymarching_frame(o, d, hits, model.density_bitfield, model.cascades, model.scale, exp_step_factor,
+                                  model.grid_size, max_samples, counter, rays_a, xyzs, dirs, deltas, ts)
+            S, dropped = counter.tolist()  # one host read per ray block
+            caps[key] = max(int(S * 1.25) + 4096, 1 << 16)
+            if dropped == 0:
+                done = True
+                xyzs, dirs, deltas, ts = xyzs[:S], dirs[:S], deltas[:S], ts[:S]
+        if not done:
+            # exact two-pass march (count -> scan -> write); also used for the first frame to learn S
+            noise = zeros[: e - b]
+            counter, rays_a = ops.raymarching_train_count(o, d, hits, model.density_bitfield, noise, model.cascades,
+                                                          model.scale, exp_step_factor, model.grid_size, max_samples)
+            S = int(counter[0].item())
+            caps[key] = max(int(S * 1.25) + 4096, 1 << 16)
+            if S > 0:
+                xyzs = torch.empty(S, 3, device=dev, dtype=torch.float32)
+                dirs = torch.empty(S, 3, device=dev, dtype=torch.float32)
+                deltas = torch.empty(S, device=dev, dtype=torch.float32)
+                ts = torch.empty(S, device=dev, dtype=torch.float32)
+                ops.raymarching_train_write(o, d, hits, model.density_bitfield, noise, model.cascades, model.scale,
+                                            exp_step_factor, model.grid_size, counter, rays_a, xyzs, dirs, deltas, ts)
         total += S
         if S == 0:
             opacity[b:e] = 0
             depth[b:e] = 0
             rgb[b:e] = 0
             continue
-        xyzs = torch.empty(S, 3, device=dev, dtype=torch.float32)
-        dirs = torch.empty(S, 3, device=dev, dtype=torch.float32)
-        deltas = torch.empty(S, device=dev, dtype=torch.float32)
-        ts = torch.empty(S, device=dev, dtype=torch.float32)
-        ops.raymarching_train_write(o, d, hits, model.density_bitfield, noise, model.cascades, model.scale,
-                                    exp_step_factor, model.grid_size, counter, rays_a, xyzs, dirs, deltas, ts)
         xn = ((xyzs - lo) / span).contiguous()
         emb = ops.hash_encode_fwd(xn, table, enc._clayout, enc.out_dim)
         sigmas, rgbs = ops.mlp_fwd(emb, dirs, W)

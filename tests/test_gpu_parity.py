@@ -462,3 +462,31 @@ def test_deployment_model_config_trains():
     before = m.pos_encoder.hash_table.detach().clone()
     loss, res = tr.step(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), torch.rand(512, 3, device='cuda'))
     assert torch.isfinite(loss) and (m.pos_encoder.hash_table != before).any()
+
+
+def test_march_frame_single_pass(ops, oracle, rays_factory, lego_bitfield):
+    """Single-pass test-time march == oracle training march with zero noise, per ray (row order is arbitrary)."""
+    n = 5003
+    o, d = rays_factory(n, seed=40)
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    ra, xyzs, dirs, deltas, ts, S = oracle.raymarching_train(o, d, hits, lego_bitfield, np.zeros(n, np.float32), 1, 0.5,
+                                                            0.0, 128, 1024)
+    cap = S + 100
+    counter = torch.zeros(2, device=DEV, dtype=torch.int32)
+    g_ra = torch.zeros(n, 3, device=DEV, dtype=torch.int32)
+    bufs = [torch.zeros(cap, 3, device=DEV), torch.zeros(cap, 3, device=DEV), torch.zeros(cap, device=DEV), torch.zeros(cap, device=DEV)]
+    ops.raymarching_frame(T(o), T(d), T(hits), T(lego_bitfield), 1, 0.5, 0.0, 128, 1024, counter, g_ra, *bufs)
+    assert N(counter).tolist() == [S, 0]
+    g_ra = N(g_ra)
+    assert np.array_equal(g_ra[:, 0], ra[:, 0]) and np.array_equal(g_ra[:, 2], ra[:, 2])
+    g_x, g_d, g_dl, g_t = [N(b) for b in bufs]
+    # gather the GPU rows back into ray order and compare bit-exactly
+    order = np.concatenate([np.arange(s0, s0 + c) for _, s0, c in g_ra if c > 0])
+    assert np.array_equal(np.sort(order), np.arange(S))  # the reserved ranges tile [0, S) exactly
+    for a, b in ((g_x, xyzs), (g_d, dirs), (g_dl, deltas), (g_t, ts)):
+        assert np.array_equal(a[order].view(np.uint32), b.view(np.uint32))
+    # capacity overflow: rays are dropped and counted, never written out of bounds
+    counter.zero_()
+    small = [torch.zeros(S // 3, 3, device=DEV), torch.zeros(S // 3, 3, device=DEV), torch.zeros(S // 3, device=DEV), torch.zeros(S // 3, device=DEV)]
+    ops.raymarching_frame(T(o), T(d), T(hits), T(lego_bitfield), 1, 0.5, 0.0, 128, 1024, counter, T(ra * 0), *small)
+    assert N(counter)[1] > 0
