@@ -100,12 +100,18 @@ def raymarching_test(rays_o, rays_d, hits_t, alive_indices, bitfield, cascades, 
 
 
 # ---- a4/a5 ---------------------------------------------------------------------------------------
-def hash_encode_fwd(xyz, table, clayout, out_dim):
+def hash_encode_fwd(xyz, table, clayout, out_dim, aabb=None):
+    """aabb = (xyz_min[3], xyz_max-xyz_min[3]) folds NGP.density's normalisation into the kernel."""
     _need_cuda(xyz, table)
     n = xyz.shape[0]
     out = torch.empty(n, out_dim, device=xyz.device, dtype=table.dtype)
-    check(load().ngp_hash_encode_fwd(_ptr(xyz), _ptr(table), C.byref(clayout), _ptr(out), _tag(table), n, _stream()),
-          "hash_encode_fwd")
+    if aabb is None:
+        check(load().ngp_hash_encode_fwd(_ptr(xyz), _ptr(table), C.byref(clayout), _ptr(out), _tag(table), n,
+                                         _stream()), "hash_encode_fwd")
+    else:
+        a6 = (C.c_float * 6)(*[float(v) for v in aabb])
+        check(load().ngp_hash_encode_fwd_dyn(_ptr(xyz), _ptr(table), C.byref(clayout), _ptr(out), _tag(table), n,
+                                             None, a6, _stream()), "hash_encode_fwd_dyn")
     return out
 
 

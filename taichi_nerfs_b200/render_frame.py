@@ -34,7 +34,7 @@ def render_frame(model, rays_o, rays_d, exp_step_factor=0.0, T_threshold=1e-4, m
     half = hasattr(enc, "table_f16")
     table = enc.table_f16() if half else enc.hash_table.detach().contiguous()
     W = [w.detach() for w in mlp_weights(model)]
-    lo, span = model.xyz_min, (model.xyz_max - model.xyz_min)
+    aabb = model.xyz_min.flatten().tolist() + (model.xyz_max - model.xyz_min).flatten().tolist()
     total = 0
     zeros = torch.zeros(min(block_rays, n), device=dev, dtype=torch.float32)  # test-time march has no jitter
     caps = model.__dict__.setdefault('_frame_capacity', {})  # learned per ray block from the previous frame
@@ -80,8 +80,7 @@ def render_frame(model, rays_o, rays_d, exp_step_factor=0.0, T_threshold=1e-4, m
             depth[b:e] = 0
             rgb[b:e] = 0
             continue
-        xn = ((xyzs - lo) / span).contiguous()
-        emb = ops.hash_encode_fwd(xn, table, enc._clayout, enc.out_dim)
+        emb = ops.hash_encode_fwd(xyzs, table, enc._clayout, enc.out_dim, aabb=aabb)  # normalisation in-kernel
         sigmas, rgbs = ops.mlp_fwd(emb, dirs, W)
         _, op_b, dp_b, rgb_b, _ = ops.composite_train_fwd(sigmas, rgbs, deltas, ts, rays_a, T_threshold)
         opacity[b:e] = op_b
