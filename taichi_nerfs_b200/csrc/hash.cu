@@ -116,38 +116,6 @@ __device__ __forceinline__ void corner_weights(const float pos[3], float w[8]) {
     for (int c = 0; c < 8; ++c) w[c] = f_mul(axy[c & 3], az[c >> 2]);
 }
 
-// Consecutive samples of a ray usually sit in the same cell or in a FACE-adjacent one.  A face move
-// along `axis` keeps 4 of the 8 corners: returns axis*2 + (step > 0) in [0,6), or -1 for any other move.
-__device__ __forceinline__ int face_move(const uint32_t g[3], const uint32_t pg[3]) {
-    const int dx = (int)(g[0] - pg[0]), dy = (int)(g[1] - pg[1]), dz = (int)(g[2] - pg[2]);
-    const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
-    if (ax + ay + az != 1) return -1;
-    return ax ? (dx > 0 ? 1 : 0) : ay ? (dy > 0 ? 3 : 2) : (dz > 0 ? 5 : 4);
-}
-// move the shared-face values to their slots in the new cell; returns the mask of corners still missing
-template <typename V>
-__device__ __forceinline__ unsigned carry_face(int mv, V v[8]) {
-    switch (mv) {
-        case 1: v[0] = v[1]; v[2] = v[3]; v[4] = v[5]; v[6] = v[7]; return 0xAAu;  // +x: need corners with x bit
-        case 0: v[1] = v[0]; v[3] = v[2]; v[5] = v[4]; v[7] = v[6]; return 0x55u;  // -x
-        case 3: v[0] = v[2]; v[1] = v[3]; v[4] = v[6]; v[5] = v[7]; return 0xCCu;  // +y
-        case 2: v[2] = v[0]; v[3] = v[1]; v[6] = v[4]; v[7] = v[5]; return 0x33u;  // -y
-        case 5: v[0] = v[4]; v[1] = v[5]; v[2] = v[6]; v[3] = v[7]; return 0xF0u;  // +z
-        case 4: v[4] = v[0]; v[5] = v[1]; v[6] = v[2]; v[7] = v[3]; return 0x0Fu;  // -z
-        default: return 0xFFu;
-    }
-}
-// for a face move: slots of the new cell filled by carried values, and old-cell corners left behind
-__device__ __forceinline__ unsigned carry_mask(int mv) {   // complement of carry_face's "missing" mask
-    const unsigned missing[6] = {0x55u, 0xAAu, 0x33u, 0xCCu, 0x0Fu, 0xF0u};
-    return 0xFFu & ~missing[mv];
-}
-__device__ __forceinline__ unsigned leave_mask(int mv) {   // old corners on the far side of the move
-    // moving +x (mv=1): old corners with x bit = 0 are left behind; -x (mv=0): x bit = 1; etc.
-    const unsigned left[6] = {0xAAu, 0x55u, 0xCCu, 0x33u, 0xF0u, 0x0Fu};
-    return left[mv];
-}
-
 template <typename T>
 struct Vec2;
 template <>
@@ -216,10 +184,7 @@ __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restr
             uint32_t g[3];
             float pos[3];
             grid_pos<kHalf>(x, m, g, pos);
-            if (!have || g[0] != pg[0] || g[1] != pg[1] || g[2] != pg[2]) {  // new cell
-                // a face-adjacent cell shares 4 corners with the previous one: keep those values in
-                // registers and gather only the missing ones
-                const unsigned need = have ? carry_face(face_move(g, pg), v) : 0xFFu;
+            if (!have || g[0] != pg[0] || g[1] != pg[1] || g[2] != pg[2]) {  // new cell: gather its 8 corners
                 have = true;
                 uint32_t idx[8];
                 corner_indices(m, g, idx);
@@ -227,16 +192,15 @@ __global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const float* __restr
                 // differ only in bit 0 (always on hashed levels with even gx: h(x+1) = h(x)^1): one load
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {
-                    const unsigned nb = (need >> c) & 3u;
-                    if (nb == 3u && (idx[c] ^ idx[c + 1]) == 1u) {
+                    if ((idx[c] ^ idx[c + 1]) == 1u) {
                         using V4 = typename Pair<V2>::type;
                         const V4 pr = __ldg(reinterpret_cast<const V4*>(tab + (idx[c] & ~1u)));
                         const V2 lo = Pair<V2>::lo(pr), hi = Pair<V2>::hi(pr);
                         v[c] = (idx[c] & 1u) ? hi : lo;
                         v[c + 1] = (idx[c] & 1u) ? lo : hi;
                     } else {
-                        if (nb & 1u) v[c] = __ldg(tab + idx[c]);
-                        if (nb & 2u) v[c + 1] = __ldg(tab + idx[c + 1]);
+                        v[c] = __ldg(tab + idx[c]);
+                        v[c + 1] = __ldg(tab + idx[c + 1]);
                     }
                 }
                 pg[0] = g[0];
@@ -344,19 +308,17 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
     uint32_t pg[3] = {0u, 0u, 0u};
     float2 acc[8];
     bool pending = false;
-    // flush the accumulators selected by `mask` (corner bit set = flush) of the cell pg
-    auto flush = [&](unsigned mask) {
+    auto flush = [&]() {
         uint32_t idx[8];
         corner_indices(m, pg, idx);
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
-            const unsigned mb = (mask >> c) & 3u;
-            if (mb == 3u && (idx[c] ^ idx[c + 1]) == 1u) {  // x-neighbours in one aligned 16-byte block: one L2 atomic
+            if ((idx[c] ^ idx[c + 1]) == 1u) {  // x-neighbours in one aligned 16-byte block: one L2 atomic
                 const float2 lo = (idx[c] & 1u) ? acc[c + 1] : acc[c], hi = (idx[c] & 1u) ? acc[c] : acc[c + 1];
                 atomicAdd(reinterpret_cast<float4*>(g2 + (idx[c] & ~1u)), make_float4(lo.x, lo.y, hi.x, hi.y));
             } else {
-                if (mb & 1u) atomicAdd(g2 + idx[c], acc[c]);  // red.global.add.v2.f32
-                if (mb & 2u) atomicAdd(g2 + idx[c + 1], acc[c + 1]);
+                atomicAdd(g2 + idx[c], acc[c]);  // red.global.add.v2.f32
+                atomicAdd(g2 + idx[c + 1], acc[c + 1]);
             }
         }
     };
@@ -374,29 +336,12 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
         float pos[3];
         grid_pos<kHalf>(x, m, g, pos);
         if (!pending || g[0] != pg[0] || g[1] != pg[1] || g[2] != pg[2]) {
-            if (pending) {
-                // face-adjacent cell: the 4 shared corners keep accumulating in registers (moved to their slots
-                // in the new cell); only the 4 corners left behind are flushed
-                const int mv = face_move(g, pg);
-                if (mv >= 0) {
-                    const unsigned keep_new = carry_mask(mv);      // slots of the NEW cell that receive carried sums
-                    flush(leave_mask(mv));                         // old-cell corners not shared
-                    carry_face(mv, acc);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (!((keep_new >> c) & 1u)) acc[c] = make_float2(0.0f, 0.0f);
-                } else {
-                    flush(0xFFu);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.0f, 0.0f);
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.0f, 0.0f);
-            }
+            if (pending) flush();
             pg[0] = g[0];
             pg[1] = g[1];
             pg[2] = g[2];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.0f, 0.0f);
             pending = true;
         }
         float w[8];
@@ -407,7 +352,7 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
             acc[c].y += w[c] * dy.y;
         }
     }
-    if (pending) flush(0xFFu);
+    if (pending) flush();
 }
 
 // ---- generic feature width (F = 1..8, e.g. the reference's --deployment config L=4 F=4) -----------
