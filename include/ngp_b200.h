@@ -104,11 +104,12 @@ int ngp_raymarching_train_write(const float* rays_o, const float* rays_d, const 
                                 float* xyzs, float* dirs, float* deltas, float* ts,
                                 int64_t n_rays, int64_t capacity, void* stream);
 
-/* Single-pass variant for test-time frames (no jitter, `0 < t` as ray_march.py:226): every ray marches
+/* Single-pass variant.  noise == NULL: test-time semantics (no jitter, `0 < t` as ray_march.py:226);
+ * noise != NULL: training semantics (ray_march.py:36-43).  Every ray marches
  * once, reserves its rows with one atomicAdd on counter[0] (caller zeroes counter[0..1]) and writes
  * rays_a[r] = (r, start, n) + its samples.  Row order across rays is arbitrary (as in the reference,
  * ray_march.py:76-81); rays that do not fit `capacity` are dropped and counted in counter[1]. */
-int ngp_raymarching_frame(const float* rays_o, const float* rays_d, const float* hits_t,
+int ngp_raymarching_frame(const float* rays_o, const float* rays_d, const float* hits_t, const float* noise,
                           const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
                           float exp_step_factor, int max_samples, int32_t* counter, int32_t* rays_a,
                           float* xyzs, float* dirs, float* deltas, float* ts, int64_t n_rays,

@@ -40,7 +40,7 @@ def _declare(lib):
         "ngp_ray_aabb_intersect": (ci, [vp, vp, f32, vp, i64, vp]),
         "ngp_raymarching_train_count": (ci, [vp, vp, vp, vp, vp, ci, ci, f32, f32, ci, vp, vp, i64, vp]),
         "ngp_raymarching_train_write": (ci, [vp, vp, vp, vp, vp, ci, ci, f32, f32, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
-        "ngp_raymarching_frame": (ci, [vp, vp, vp, vp, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
+        "ngp_raymarching_frame": (ci, [vp, vp, vp, vp, vp, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
         "ngp_raymarching_test": (ci, [vp, vp, vp, vp, vp, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, i64, vp]),
         "ngp_hash_encode_fwd": (ci, [vp, vp, lay, vp, ci, i64, vp]),
         "ngp_hash_encode_bwd": (ci, [vp, vp, ci, lay, vp, i64, vp]),

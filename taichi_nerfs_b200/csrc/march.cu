@@ -238,8 +238,13 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
     Ray ray;
     load_ray(rays_o, rays_d, r, ray);
     const float t2 = hits_t[r * 2 + 1];
-    float t = kMode == 2 ? hits_t[r * 2 + 0] : train_t0(hits_t, noise, r, p);  // test time: no jitter
-    if (kMode == 2 && !(0.0f < t)) t = -1.0f;                                   // ray_march.py:226 (strict 0 < t)
+    float t;
+    if (kMode == 2 && noise == nullptr) {  // test time: no jitter, strict 0 < t (ray_march.py:226)
+        t = hits_t[r * 2 + 0];
+        if (!(0.0f < t)) t = -1.0f;
+    } else {
+        t = train_t0(hits_t, noise, r, p);
+    }
     int emitted = 0;
     float skip_until = -INFINITY;
     const bool const_dt = p.esf == 0.0f;
@@ -511,7 +516,7 @@ int ngp_raymarching_train_write(const float* rays_o, const float* rays_d, const 
     return 0;
 }
 
-int ngp_raymarching_frame(const float* rays_o, const float* rays_d, const float* hits_t,
+int ngp_raymarching_frame(const float* rays_o, const float* rays_d, const float* hits_t, const float* noise,
                           const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
                           float exp_step_factor, int max_samples, int32_t* counter, int32_t* rays_a, float* xyzs,
                           float* dirs, float* deltas, float* ts, int64_t n_rays, int64_t capacity, void* stream) {
@@ -523,7 +528,7 @@ int ngp_raymarching_frame(const float* rays_o, const float* rays_d, const float*
     const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
     const unsigned grid = (unsigned)((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
     march_train_warp_kernel<2><<<grid, kRaysPerBlock * 32, 0, ngp::as_stream(stream)>>>(
-        rays_o, rays_d, hits_t, nullptr, p, max_samples, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity);
+        rays_o, rays_d, hits_t, noise, p, max_samples, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity);
     NGP_LAUNCHED("march_train_warp_kernel<frame>");
     return 0;
 }

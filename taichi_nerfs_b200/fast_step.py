@@ -100,13 +100,13 @@ class StaticTrainStep:
         tag = F16 if self.half else F32
         bits = m.density_bitfield
         check(L.ngp_ray_aabb_intersect(_p(self.rays_o), _p(self.rays_d), float(m.scale), _p(self.hits), n, st))
-        check(L.ngp_raymarching_train_count(_p(self.rays_o), _p(self.rays_d), _p(self.hits), _p(bits), _p(self.noise),
-                                            m.cascades, m.grid_size, float(m.scale), self.esf, self.max_samples,
-                                            _p(self.counter), _p(self.rays_a), n, st))
-        check(L.ngp_raymarching_train_write(_p(self.rays_o), _p(self.rays_d), _p(self.hits), _p(bits), _p(self.noise),
-                                            m.cascades, m.grid_size, float(m.scale), self.esf, _p(self.counter),
-                                            _p(self.rays_a), _p(self.xyzs), _p(self.dirs), _p(self.deltas), _p(self.ts),
-                                            n, cap, st))
+        # single-pass march: every ray reserves its rows with one atomic (row order across rays is arbitrary, as
+        # in the reference's atomics at ray_march.py:76-81; the module API keeps the deterministic two-pass layout)
+        self.counter.zero_()
+        check(L.ngp_raymarching_frame(_p(self.rays_o), _p(self.rays_d), _p(self.hits), _p(self.noise), _p(bits),
+                                      m.cascades, m.grid_size, float(m.scale), self.esf, self.max_samples,
+                                      _p(self.counter), _p(self.rays_a), _p(self.xyzs), _p(self.dirs),
+                                      _p(self.deltas), _p(self.ts), n, cap, st))
         nd = _p(self.counter)  # counter[0] = number of valid sample rows, read on the device
         check(L.ngp_hash_encode_fwd_dyn(_p(self.xyzs), _p(self._table()), C.byref(self._clayout), _p(self.emb), tag,
                                         cap, nd, self.aabb6, st))

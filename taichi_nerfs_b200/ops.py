@@ -79,10 +79,11 @@ def raymarching_train_write(rays_o, rays_d, hits_t, bitfield, noise, cascades, s
 
 
 def raymarching_frame(rays_o, rays_d, hits_t, bitfield, cascades, scale, exp_step_factor, grid_size, max_samples,
-                      counter, rays_a, xyzs, dirs, deltas, ts):
-    """Single-pass test-time march into capacity buffers; counter = [rows reserved, rays dropped]."""
+                      counter, rays_a, xyzs, dirs, deltas, ts, noise=None):
+    """Single-pass march into capacity buffers; counter = [rows reserved, rays dropped] (caller zeroes it).
+    noise=None: test-time semantics; noise tensor: training semantics (jittered start)."""
     n, cap = rays_o.shape[0], deltas.shape[0]
-    check(load().ngp_raymarching_frame(_ptr(rays_o), _ptr(rays_d), _ptr(hits_t), _ptr(bitfield), int(cascades),
+    check(load().ngp_raymarching_frame(_ptr(rays_o), _ptr(rays_d), _ptr(hits_t), _ptr(noise), _ptr(bitfield), int(cascades),
                                        int(grid_size), float(scale), float(exp_step_factor), int(max_samples),
                                        _ptr(counter), _ptr(rays_a), _ptr(xyzs), _ptr(dirs), _ptr(deltas), _ptr(ts),
                                        n, cap, _stream()), "raymarching_frame")

@@ -151,7 +151,8 @@ def test_static_step_capacity_overflow_is_safe(lego_bitfield):
     fs = StaticTrainStep(NGPTrainer(m), n, samples_per_ray_capacity=32, use_graph=True)
     loss = fs.step(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), torch.rand(n, 3, device='cuda'))
     assert torch.isfinite(loss).all()
-    assert 0 < int(fs.counter[0]) <= fs.cap
+    reserved, dropped = fs.counter.tolist()
+    assert reserved > fs.cap and dropped > 0   # rays that did not fit were dropped and counted, never written
     assert all(torch.isfinite(p).all() for p in m.parameters())
 
 
