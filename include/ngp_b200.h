@@ -172,11 +172,20 @@ int ngp_adam_step_dyn(float* param, float* grad, float* exp_avg, float* exp_avg_
  * Adam bias corrections for t = step+1 (train.py:143-156). */
 int ngp_adam_hyper_update(int32_t* step_dev, float lr0, float lr_min, int32_t max_steps, float beta1,
                           float beta2, float inv_scale, float* hyper_dev, void* stream);
+/* torch.cuda.amp.GradScaler.update() on the device (train.py:137-141,200): state_dev = {scale, growth_tracker};
+ * found_inf != 0 -> scale *= backoff, tracker = 0; else tracker += 1 and, every growth_interval clean steps,
+ * scale *= growth.  Also refreshes hyper_dev[2] = 1 / (scale * world_size) for the NEXT step's Adam. */
+int ngp_loss_scale_update(float* state_dev, const int32_t* found_inf, float growth, float backoff,
+                          int32_t growth_interval, float world_size, float* hyper_dev, void* stream);
 /* per-ray loss head: out = rgb + bg*(1-opacity) (modules/rendering.py:219-226), loss = mean((out-gt)^2)
  * (train.py:193), and d(loss*loss_scale)/d rgb, /d opacity in one launch.  *loss_sum accumulates
  * sum((out-gt)^2) (caller zeroes it; divide by 3*n_rays). */
 int ngp_mse_loss_grad(const float* rgb, const float* opacity, const float* gt, float bg, float loss_scale,
                       float* loss_sum, float* g_rgb, float* g_opacity, int64_t n_rays, void* stream);
+/* same with the loss scale read from device memory (scale_dev[0]); loss_scale is ignored */
+int ngp_mse_loss_grad_dyn(const float* rgb, const float* opacity, const float* gt, float bg,
+                          const float* scale_dev, float* loss_sum, float* g_rgb, float* g_opacity,
+                          int64_t n_rays, void* stream);
 
 /* ---- a6: spherical-harmonics direction encoding -------------------------- */
 /* replaces dir_encoder, modules/spherical_harmonics.py:7-42 */

@@ -85,8 +85,30 @@ __global__ void adam_hyper_kernel(int32_t* __restrict__ step_dev, float lr0, flo
     const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
     hyper[0] = (float)(lr / bc1);
     hyper[1] = (float)sqrt(bc2);
-    hyper[2] = inv_scale;
+    if (inv_scale > 0.0f) hyper[2] = inv_scale;  // <= 0: leave the value maintained by ngp_loss_scale_update
     *step_dev = s + 1;
+}
+
+// GradScaler.update(): torch/amp/grad_scaler.py -> _amp_update_scale_
+__global__ void loss_scale_update_kernel(float* __restrict__ state, const int32_t* __restrict__ found_inf, float growth,
+                                         float backoff, int32_t interval, float world, float* __restrict__ hyper) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float scale = state[0];
+    int32_t tracker = __float_as_int(state[1]);
+    if (found_inf != nullptr && *found_inf != 0) {
+        scale *= backoff;
+        tracker = 0;
+    } else {
+        tracker += 1;
+        if (tracker >= interval) {
+            const float grown = scale * growth;
+            if (grown < INFINITY) scale = grown;
+            tracker = 0;
+        }
+    }
+    state[0] = scale;
+    state[1] = __int_as_float(tracker);
+    if (hyper != nullptr) hyper[2] = 1.0f / (scale * world);
 }
 
 __global__ void __launch_bounds__(256) check_finite_kernel(const float* __restrict__ grad, int64_t n,
@@ -171,6 +193,16 @@ int ngp_adam_hyper_update(int32_t* step_dev, float lr0, float lr_min, int32_t ma
     adam_hyper_kernel<<<1, 32, 0, ngp::as_stream(stream)>>>(step_dev, lr0, lr_min, max_steps, beta1, beta2, inv_scale,
                                                             hyper_dev);
     NGP_LAUNCHED("adam_hyper_kernel");
+    return 0;
+}
+
+int ngp_loss_scale_update(float* state_dev, const int32_t* found_inf, float growth, float backoff,
+                          int32_t growth_interval, float world_size, float* hyper_dev, void* stream) {
+    NGP_REQUIRE(state_dev != nullptr, "null pointer");
+    NGP_REQUIRE(growth >= 1.0f && backoff > 0.0f && backoff <= 1.0f && growth_interval >= 1, "bad GradScaler constants");
+    loss_scale_update_kernel<<<1, 32, 0, ngp::as_stream(stream)>>>(state_dev, found_inf, growth, backoff, growth_interval,
+                                                                   world_size, hyper_dev);
+    NGP_LAUNCHED("loss_scale_update_kernel");
     return 0;
 }
 

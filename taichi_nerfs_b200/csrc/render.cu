@@ -270,9 +270,11 @@ composite_test_kernel(const float* __restrict__ sigmas, const TRgb* __restrict__
 // gradients of loss*loss_scale wrt the compositing outputs, in one launch instead of ~8 torch ops.
 __global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ opacity,
                                                             const float* __restrict__ gt, float bg, float coef,
+                                                            const float* __restrict__ scale_dev,
                                                             float* __restrict__ loss_sum, float* __restrict__ g_rgb,
                                                             float* __restrict__ g_op, int64_t n_rays) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (scale_dev != nullptr) coef *= *scale_dev;  // coef was built with scale 1
     float sq = 0.f;
     if (r < n_rays) {
         const float keep = bg * (1.0f - opacity[r]);
@@ -369,7 +371,19 @@ int ngp_mse_loss_grad(const float* rgb, const float* opacity, const float* gt, f
     NGP_REQUIRE(rgb && opacity && gt && loss_sum && g_rgb && g_opacity, "null pointer");
     const float coef = loss_scale * 2.0f / (3.0f * (float)n_rays);
     mse_loss_grad_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, ngp::as_stream(stream)>>>(
-        rgb, opacity, gt, bg, coef, loss_sum, g_rgb, g_opacity, n_rays);
+        rgb, opacity, gt, bg, coef, nullptr, loss_sum, g_rgb, g_opacity, n_rays);
+    NGP_LAUNCHED("mse_loss_grad_kernel");
+    return 0;
+}
+
+int ngp_mse_loss_grad_dyn(const float* rgb, const float* opacity, const float* gt, float bg, const float* scale_dev,
+                          float* loss_sum, float* g_rgb, float* g_opacity, int64_t n_rays, void* stream) {
+    NGP_REQUIRE(n_rays >= 0, "negative n_rays");
+    if (n_rays == 0) return 0;
+    NGP_REQUIRE(rgb && opacity && gt && loss_sum && g_rgb && g_opacity && scale_dev, "null pointer");
+    const float coef = 2.0f / (3.0f * (float)n_rays);
+    mse_loss_grad_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, ngp::as_stream(stream)>>>(
+        rgb, opacity, gt, bg, coef, scale_dev, loss_sum, g_rgb, g_opacity, n_rays);
     NGP_LAUNCHED("mse_loss_grad_kernel");
     return 0;
 }

@@ -29,7 +29,8 @@ def _p(t):
 
 class StaticTrainStep:
     def __init__(self, trainer, n_rays: int, samples_per_ray_capacity: int = 384, exp_step_factor: float = 0.0,
-                 T_threshold: float = 1e-4, max_samples: int = 1024, use_graph: bool = True):
+                 T_threshold: float = 1e-4, max_samples: int = 1024, use_graph: bool = True,
+                 dynamic_loss_scale: bool = True):
         self.tr = trainer
         m = self.model = trainer.model
         enc = m.pos_encoder
@@ -60,6 +61,10 @@ class StaticTrainStep:
         # optimizer scalars on the device
         self.step_dev = torch.full((1,), trainer.step_count, device=dev, dtype=i32)
         self.hyper = z(3)
+        # GradScaler state on the device: [scale, growth_tracker (int bits)]; growth 2x / 2000 clean steps, backoff 0.5
+        self.dynamic_loss_scale = bool(dynamic_loss_scale)
+        self.scale_state = torch.tensor([trainer.loss_scale, 0.0], device=dev, dtype=f32)
+        self.hyper[2] = parallel.inv_grad_scale(trainer.loss_scale, trainer.world_size)
         self.aabb6 = (C.c_float * 6)(*[float(v) for v in m.xyz_min.flatten().tolist()],
                                      *[float(v) for v in (m.xyz_max - m.xyz_min).flatten().tolist()])
         self._clayout = enc._clayout
@@ -117,8 +122,12 @@ class StaticTrainStep:
                                         _p(self.ws), n, cap, st))
         self.loss_sum.zero_()
         bg = 1.0 if self.esf == 0 else 0.0
-        check(L.ngp_mse_loss_grad(_p(self.rgb), _p(self.opacity), _p(self.gt), bg, float(self.tr.loss_scale),
-                                  _p(self.loss_sum), _p(self.g_rgb), _p(self.g_op), n, st))
+        if self.dynamic_loss_scale:
+            check(L.ngp_mse_loss_grad_dyn(_p(self.rgb), _p(self.opacity), _p(self.gt), bg, _p(self.scale_state),
+                                          _p(self.loss_sum), _p(self.g_rgb), _p(self.g_op), n, st))
+        else:
+            check(L.ngp_mse_loss_grad(_p(self.rgb), _p(self.opacity), _p(self.gt), bg, float(self.tr.loss_scale),
+                                      _p(self.loss_sum), _p(self.g_rgb), _p(self.g_op), n, st))
         check(L.ngp_composite_train_bwd(_p(self.g_op), _p(self.g_depth), _p(self.g_rgb), None, _p(self.sig),
                                         _p(self.rgbs), F16, _p(self.deltas), _p(self.ts), _p(self.rays_a), None, None,
                                         None, self.T_thr, _p(self.dsig), _p(self.drgbs), n, cap, st))
@@ -134,7 +143,8 @@ class StaticTrainStep:
         fg = tr.flat_grad
         tr.found_inf.zero_()
         check(L.ngp_check_finite(_p(fg), fg.numel(), _p(tr.found_inf), st))
-        inv = parallel.inv_grad_scale(tr.loss_scale, tr.world_size)
+        # inv_scale: static (host constant) or the device value maintained by ngp_loss_scale_update (-1 sentinel)
+        inv = -1.0 if self.dynamic_loss_scale else parallel.inv_grad_scale(tr.loss_scale, tr.world_size)
         check(L.ngp_adam_hyper_update(_p(self.step_dev), tr.lr0, tr.lr0 / 30, tr.max_steps, tr.betas[0], tr.betas[1],
                                       inv, _p(self.hyper), st))
         enc = self.model.pos_encoder
@@ -143,6 +153,9 @@ class StaticTrainStep:
             check(L.ngp_adam_step_dyn(_p(p.data), _p(fg[off:off + s]), _p(tr.exp_avg[off:off + s]),
                                       _p(tr.exp_avg_sq[off:off + s]), _p(shadow), _p(tr.found_inf), _p(self.hyper),
                                       tr.betas[0], tr.betas[1], tr.eps, 1, s, st))
+        if self.dynamic_loss_scale:  # GradScaler.update(): adjusts the scale used by the NEXT step
+            check(L.ngp_loss_scale_update(_p(self.scale_state), _p(tr.found_inf), 2.0, 0.5, 2000, float(tr.world_size),
+                                          _p(self.hyper), st))
 
     def _enqueue(self):
         self._enqueue_forward_backward()
@@ -154,6 +167,7 @@ class StaticTrainStep:
         # the graph must not mutate training state while being built: snapshot, warm up + capture, restore
         tr = self.tr
         keep = [p.data.clone() for p in tr.params] + [tr.exp_avg.clone(), tr.exp_avg_sq.clone(), self.step_dev.clone()]
+        scale_keep, hyper_keep = self.scale_state.clone(), self.hyper.clone()
         shadow = None if tr._shadow is None else tr._shadow.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -173,6 +187,8 @@ class StaticTrainStep:
         tr.exp_avg.copy_(keep[-3])
         tr.exp_avg_sq.copy_(keep[-2])
         self.step_dev.copy_(keep[-1])
+        self.scale_state.copy_(scale_keep)
+        self.hyper.copy_(hyper_keep)
         tr.flat_grad.zero_()
         if shadow is not None:
             tr._shadow.copy_(shadow)

@@ -195,3 +195,33 @@ def test_static_step_other_configs(cfg, monkeypatch):
         assert abs(a - b) < 3e-3 * max(a, 1e-6), (l1, l2)
     for p1, p2 in zip(m1.parameters(), m2.parameters()):
         assert float(((p1 - p2).abs() > 2e-3).float().mean()) < 5e-3
+
+
+def test_device_side_grad_scaler(lego_bitfield):
+    """GradScaler semantics on the device: an overflowing step is skipped and halves the scale; clean steps count
+    towards the growth interval."""
+    from modules.networks import NGP
+    from oracle.train_step import make_rays
+    from taichi_nerfs_b200.fast_step import StaticTrainStep
+    from taichi_nerfs_b200.trainer import NGPTrainer
+    torch.manual_seed(3)
+    m = NGP(scale=0.5, max_res=1024, half_opt=True).cuda()
+    with torch.no_grad():
+        m.pos_encoder.hash_table.mul_(2e3)
+        m.density_bitfield.copy_(torch.from_numpy(lego_bitfield))
+    n = 1024
+    o, d = make_rays(n, seed=14)
+    o, d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    fs = StaticTrainStep(NGPTrainer(m), n, samples_per_ray_capacity=64, use_graph=True)
+    assert float(fs.scale_state[0]) == 65536.0
+    fs.step(o, d, torch.rand(n, 3, device='cuda'))
+    assert float(fs.scale_state[0]) == 65536.0 and int(fs.scale_state[1:].view(torch.int32)) == 1
+    before = [p.detach().clone() for p in m.parameters()]
+    fs.step(o, d, torch.full((n, 3), float('nan'), device='cuda'))     # poisoned targets -> non-finite gradients
+    assert float(fs.scale_state[0]) == 32768.0 and int(fs.scale_state[1:].view(torch.int32)) == 0
+    for p, b in zip(m.parameters(), before):
+        assert torch.equal(p, b)                                         # the step was skipped
+    assert abs(float(fs.hyper[2]) - 1 / 32768.0) < 1e-12
+    fs.step(o, d, torch.rand(n, 3, device='cuda'))                      # training continues with the halved scale
+    assert all(torch.isfinite(p).all() for p in m.parameters())
+    assert any(not torch.equal(p, b) for p, b in zip(m.parameters(), before))
