@@ -235,6 +235,15 @@ int ngp_composite_test(const float* sigmas, const void* rgbs, int rgbs_dtype,
                        float* opacity, float* depth, float* rgb,
                        int64_t n_alive, void* stream);
 
+/* Fused per-ray head used by the graph-captured step: composite forward (volume_train.py:6-48) + background +
+ * MSE (rendering.py:219-226, train.py:193) + composite backward in ONE launch.  gt is indexed by ray id;
+ * loss scale = scale_dev[0] if scale_dev != NULL else loss_scale; *loss_sum accumulates sum((out-gt)^2);
+ * opacity_out / rgb_out may be NULL. */
+int ngp_ray_head_fused(const float* sigmas, const void* rgbs, int rgbs_dtype, const float* deltas,
+                       const int32_t* rays_a, const float* gt, float bg, float loss_scale,
+                       const float* scale_dev, float T_threshold, float* loss_sum, float* opacity_out,
+                       float* rgb_out, float* dL_dsigmas, void* dL_drgbs, int64_t n_rays, void* stream);
+
 /* ---- distortion loss -------------------------------------- */
 /* replaces prefix_sums_kernel + _loss_kernel + distortion_loss_fw_kernel
  * (modules/distortion.py:15-84): loss[ray] = sum_s 2*(wts_inc*ws_exc - ws_inc*wts_exc) + w^2*delta/3

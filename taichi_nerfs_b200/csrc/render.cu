@@ -293,6 +293,144 @@ __global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restr
     if ((threadIdx.x & 31) == 0 && sq != 0.f) atomicAdd(loss_sum, sq);
 }
 
+// ---- fused per-ray head for the graph-captured step: composite forward + MSE loss + composite backward ------
+// One warp per ray does what composite_train_fwd_kernel, mse_loss_grad_kernel and composite_train_bwd_kernel do
+// in three launches: the ray's samples are read from HBM once (the reverse pass hits L1/L2), and the
+// per-sample ws / per-ray depth that the loss does not need are never written.
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ray_head_fused_kernel(const float* __restrict__ sigmas, const T* __restrict__ rgbs, const float* __restrict__ deltas,
+                      const int32_t* __restrict__ rays_a, const float* __restrict__ gt, float bg, float coef,
+                      const float* __restrict__ scale_dev, float thr, float* __restrict__ loss_sum,
+                      float* __restrict__ opacity_out, float* __restrict__ rgb_out, float* __restrict__ dsigmas,
+                      T* __restrict__ drgbs, int64_t n_rays) {
+    __shared__ float Tstart_s[kWarpsPerBlock][kChunkCap];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t n = (int64_t)blockIdx.x * kWarpsPerBlock + wid;
+    if (n >= n_rays) return;
+    if (scale_dev != nullptr) coef *= *scale_dev;
+    const int64_t ray = rays_a[n * 3 + 0], start = rays_a[n * 3 + 1];
+    const int N = rays_a[n * 3 + 2];
+    float* Tstart = Tstart_s[wid];
+
+    // forward: colour / opacity sums, transmittance at every chunk start, last active chunk
+    const int n_chunks = (N + 31) >> 5;
+    int last_chunk = -1;
+    float r = 0.f, g = 0.f, b = 0.f, op = 0.f;
+    {
+        float Tc = 1.0f;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int k = c * 32 + lane;
+            const bool valid = k < N;
+            const int64_t s = start + k;
+            float a = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            if (valid) {
+                a = 1.0f - expf(-sigmas[s] * deltas[s]);
+                c0 = load_as_float(rgbs, s * 3 + 0);
+                c1 = load_as_float(rgbs, s * 3 + 1);
+                c2 = load_as_float(rgbs, s * 3 + 2);
+            }
+            const float incl = warp_scan_mul(1.0f - a, lane);
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            const float Tb = Tc * excl;
+            const bool active = valid && Tb > thr;
+            const float w = active ? a * Tb : 0.0f;
+            r += w * c0;
+            g += w * c1;
+            b += w * c2;
+            op += w;
+            const unsigned act = __ballot_sync(0xffffffffu, active);
+            const unsigned val = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0 && c < kChunkCap) Tstart[c] = Tc;
+            if (act) last_chunk = c;
+            if (act != val) {  // terminated inside this chunk: zero the tail's gradients
+                for (int c2i = c; c2i < n_chunks; ++c2i) {
+                    const int k2 = c2i * 32 + lane;
+                    if (k2 < N && !(c2i == c && active)) {
+                        const int64_t s2 = start + k2;
+                        dsigmas[s2] = 0.0f;
+                        store_from_float(drgbs, s2 * 3 + 0, 0.0f);
+                        store_from_float(drgbs, s2 * 3 + 1, 0.0f);
+                        store_from_float(drgbs, s2 * 3 + 2, 0.0f);
+                    }
+                }
+                break;
+            }
+            Tc = Tc * __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    r = warp_sum(r);
+    g = warp_sum(g);
+    b = warp_sum(b);
+    op = warp_sum(op);
+    // loss head (rendering.py:219-226, train.py:193)
+    const float keep = bg * (1.0f - op);
+    const float d0 = r + keep - gt[ray * 3 + 0], d1 = g + keep - gt[ray * 3 + 1], d2 = b + keep - gt[ray * 3 + 2];
+    const float gr = coef * d0, gg = coef * d1, gb = coef * d2;
+    const float go = -bg * (gr + gg + gb);
+    if (lane == 0) {
+        atomicAdd(loss_sum, d0 * d0 + d1 * d1 + d2 * d2);
+        if (opacity_out) opacity_out[ray] = op;
+        if (rgb_out) {
+            rgb_out[ray * 3 + 0] = r + keep;
+            rgb_out[ray * 3 + 1] = g + keep;
+            rgb_out[ray * 3 + 2] = b + keep;
+        }
+    }
+    __syncwarp();
+
+    // backward: exact reverse suffix accumulation (same as composite_train_bwd_kernel with g_depth = g_ws = 0)
+    float suffix = 0.0f;
+    for (int c = last_chunk; c >= 0; --c) {
+        float Tc;
+        if (c < kChunkCap) {
+            Tc = Tstart[c];
+        } else {
+            Tc = Tstart[kChunkCap - 1];
+            for (int c2i = kChunkCap - 1; c2i < c; ++c2i) {
+                const int k2 = c2i * 32 + lane;
+                const float a2 = k2 < N ? 1.0f - expf(-sigmas[start + k2] * deltas[start + k2]) : 0.0f;
+                const float in2 = warp_scan_mul(1.0f - a2, lane);
+                Tc = Tc * __shfl_sync(0xffffffffu, in2, 31);
+            }
+        }
+        const int k = c * 32 + lane;
+        const bool valid = k < N;
+        const int64_t s = start + k;
+        float a = 0.f, dl = 0.f, c0 = 0.f, c1 = 0.f, c2v = 0.f;
+        if (valid) {
+            dl = deltas[s];
+            a = 1.0f - expf(-sigmas[s] * dl);
+            c0 = load_as_float(rgbs, s * 3 + 0);
+            c1 = load_as_float(rgbs, s * 3 + 1);
+            c2v = load_as_float(rgbs, s * 3 + 2);
+        }
+        const float incl = warp_scan_mul(1.0f - a, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        const float Tb = Tc * excl;
+        const bool active = valid && Tb > thr;
+        const float w = active ? a * Tb : 0.0f;
+        const float G = gr * c0 + gg * c1 + gb * c2v + go;
+        const float wG = w * G;
+        float rs = wG;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float nb = __shfl_down_sync(0xffffffffu, rs, o);
+            if (lane + o < 32) rs += nb;
+        }
+        const float later = suffix + (rs - wG);
+        if (active) {
+            dsigmas[s] = dl * (Tb * (1.0f - a) * G - later);
+            store_from_float(drgbs, s * 3 + 0, w * gr);
+            store_from_float(drgbs, s * 3 + 1, w * gg);
+            store_from_float(drgbs, s * 3 + 2, w * gb);
+        }
+        suffix += __shfl_sync(0xffffffffu, rs, 0);
+    }
+}
+
 // ---- distortion loss (Mip-NeRF 360), modules/distortion.py:15-119 -----------------------------------
 // warp per ray; per-ray scans of w and w*t are warp prefix sums carried across 32-sample chunks
 // (the reference's TODO at distortion.py:4-6 asks for exactly this shared/warp scan).
@@ -385,6 +523,29 @@ int ngp_mse_loss_grad_dyn(const float* rgb, const float* opacity, const float* g
     mse_loss_grad_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, ngp::as_stream(stream)>>>(
         rgb, opacity, gt, bg, coef, scale_dev, loss_sum, g_rgb, g_opacity, n_rays);
     NGP_LAUNCHED("mse_loss_grad_kernel");
+    return 0;
+}
+
+int ngp_ray_head_fused(const float* sigmas, const void* rgbs, int rgbs_dtype, const float* deltas, const int32_t* rays_a,
+                       const float* gt, float bg, float loss_scale, const float* scale_dev, float T_threshold,
+                       float* loss_sum, float* opacity_out, float* rgb_out, float* dL_dsigmas, void* dL_drgbs,
+                       int64_t n_rays, void* stream) {
+    NGP_REQUIRE(n_rays >= 0, "negative n_rays");
+    NGP_REQUIRE(rgbs_dtype == NGP_F32 || rgbs_dtype == NGP_F16, "bad dtype");
+    if (n_rays == 0) return 0;
+    NGP_REQUIRE(sigmas && rgbs && deltas && rays_a && gt && loss_sum && dL_dsigmas && dL_drgbs, "null pointer");
+    const float coef = (scale_dev ? 1.0f : loss_scale) * 2.0f / (3.0f * (float)n_rays);
+    const unsigned grid = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    cudaStream_t st = ngp::as_stream(stream);
+    if (rgbs_dtype == NGP_F16)
+        ray_head_fused_kernel<__half><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+            sigmas, (const __half*)rgbs, deltas, rays_a, gt, bg, coef, scale_dev, T_threshold, loss_sum, opacity_out,
+            rgb_out, dL_dsigmas, (__half*)dL_drgbs, n_rays);
+    else
+        ray_head_fused_kernel<float><<<grid, kWarpsPerBlock * 32, 0, st>>>(
+            sigmas, (const float*)rgbs, deltas, rays_a, gt, bg, coef, scale_dev, T_threshold, loss_sum, opacity_out,
+            rgb_out, dL_dsigmas, (float*)dL_drgbs, n_rays);
+    NGP_LAUNCHED("ray_head_fused_kernel");
     return 0;
 }
 

@@ -117,20 +117,13 @@ class StaticTrainStep:
                                         cap, nd, self.aabb6, st))
         check(L.ngp_mlp_fwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.sig), _p(self.rgbs),
                                 cap, nd, st))
-        check(L.ngp_composite_train_fwd(_p(self.sig), _p(self.rgbs), F16, _p(self.deltas), _p(self.ts), _p(self.rays_a),
-                                        self.T_thr, _p(self.total), _p(self.opacity), _p(self.depth), _p(self.rgb),
-                                        _p(self.ws), n, cap, st))
+        # composite forward + background + MSE + composite backward in one launch (per-ray work)
         self.loss_sum.zero_()
         bg = 1.0 if self.esf == 0 else 0.0
-        if self.dynamic_loss_scale:
-            check(L.ngp_mse_loss_grad_dyn(_p(self.rgb), _p(self.opacity), _p(self.gt), bg, _p(self.scale_state),
-                                          _p(self.loss_sum), _p(self.g_rgb), _p(self.g_op), n, st))
-        else:
-            check(L.ngp_mse_loss_grad(_p(self.rgb), _p(self.opacity), _p(self.gt), bg, float(self.tr.loss_scale),
-                                      _p(self.loss_sum), _p(self.g_rgb), _p(self.g_op), n, st))
-        check(L.ngp_composite_train_bwd(_p(self.g_op), _p(self.g_depth), _p(self.g_rgb), None, _p(self.sig),
-                                        _p(self.rgbs), F16, _p(self.deltas), _p(self.ts), _p(self.rays_a), None, None,
-                                        None, self.T_thr, _p(self.dsig), _p(self.drgbs), n, cap, st))
+        check(L.ngp_ray_head_fused(_p(self.sig), _p(self.rgbs), F16, _p(self.deltas), _p(self.rays_a), _p(self.gt), bg,
+                                   float(self.tr.loss_scale), _p(self.scale_state) if self.dynamic_loss_scale else None,
+                                   self.T_thr, _p(self.loss_sum), _p(self.opacity), _p(self.rgb), _p(self.dsig),
+                                   _p(self.drgbs), n, st))
         fg = self.tr.flat_grad
         gw = fg[self.P:self.P + 9408]
         check(L.ngp_mlp_bwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.dsig), _p(self.drgbs),

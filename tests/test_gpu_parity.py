@@ -490,3 +490,36 @@ def test_march_frame_single_pass(ops, oracle, rays_factory, lego_bitfield):
     small = [torch.zeros(S // 3, 3, device=DEV), torch.zeros(S // 3, 3, device=DEV), torch.zeros(S // 3, device=DEV), torch.zeros(S // 3, device=DEV)]
     ops.raymarching_frame(T(o), T(d), T(hits), T(lego_bitfield), 1, 0.5, 0.0, 128, 1024, counter, T(ra * 0), *small)
     assert N(counter)[1] > 0
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_ray_head_fused_equals_separate_kernels(ops, oracle, dense):
+    """composite fwd + bg + MSE + composite bwd in one launch == the three separate kernels == the oracle."""
+    import ctypes as C
+    from taichi_nerfs_b200 import _lib
+    rng = np.random.default_rng(41)
+    rays_a, sig, rgbs, deltas, ts = _composite_inputs(rng, 500, 200, dense, True)
+    rays_a[:, 0] = np.arange(500)
+    n, S = rays_a.shape[0], sig.shape[0]
+    gt = rng.random((n, 3)).astype(np.float32)
+    scale = 1024.0
+    tot, op, dep, rgb, ws = oracle.composite_train_fwd(sig, rgbs, deltas, ts, rays_a, 1e-4)
+    out = rgb + (1 - op)[:, None]
+    diff = out - gt
+    g_rgb = (scale * 2 * diff / (3 * n)).astype(np.float32)
+    g_op = -g_rgb.sum(1)
+    dsig_ref, drgbs_ref = oracle.composite_train_bwd(g_op, np.zeros(n, np.float32), g_rgb, np.zeros(S, np.float32),
+                                                     sig, rgbs, deltas, ts, rays_a, 1e-4)
+    t_sig, t_rgbs, t_dl, t_ra, t_gt = T(sig), T(rgbs), T(deltas), T(rays_a), T(gt)
+    loss_sum = torch.zeros(1, device=DEV)
+    o_op, o_rgb = torch.zeros(n, device=DEV), torch.zeros(n, 3, device=DEV)
+    dsig, drgbs = torch.zeros(S, device=DEV), torch.zeros(S, 3, device=DEV, dtype=torch.float16)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.load().ngp_ray_head_fused(p(t_sig), p(t_rgbs), 1, p(t_dl), p(t_ra), p(t_gt), 1.0, scale, None, 1e-4,
+                                              p(loss_sum), p(o_op), p(o_rgb), p(dsig), p(drgbs), n, st))
+    np.testing.assert_allclose(N(o_op), op, atol=2e-5)
+    np.testing.assert_allclose(N(o_rgb), out, atol=3e-5)
+    assert abs(float(loss_sum) - float((diff.astype(np.float64) ** 2).sum())) < 1e-3 * float((diff ** 2).sum())
+    assert np.abs(N(dsig) - dsig_ref).max() <= 2e-3 * np.abs(dsig_ref).max()
+    assert np.abs(N(drgbs).astype(np.float32) - drgbs_ref.astype(np.float32)).max() <= 3e-3 * max(1.0, np.abs(drgbs_ref.astype(np.float32)).max())
