@@ -24,7 +24,9 @@
 namespace {
 
 constexpr int kTile = 128;          // samples per tile == UMMA M
-constexpr int kThreads = 128;       // one thread per sample row / TMEM lane
+constexpr int kRows = 128;          // sample rows per tile == TMEM lanes
+constexpr int kThreads = 256;       // TWO threads per row: warps 0-3 own accumulator columns [0,32), warps 4-7 own [32,64)
+                                    // (a warp may touch TMEM lanes 32*(warp%4)..+31), halving every epilogue's latency
 constexpr uint32_t kTmemCols = 64;  // fp32 accumulator columns (max N = 64)
 
 // shared memory map (bytes).  Weights first (shared by both kernels), then activation buffers.
@@ -119,16 +121,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// all 64 accumulator columns of this thread's row with a single wait (the four loads pipeline)
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float v[64]) {
-    uint32_t r[64];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) tmem_ld16_issue(taddr + g * 16, r + g * 16);
+// 32 accumulator columns (two pipelined loads, one wait)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+    uint32_t r[32];
+    tmem_ld16_issue(taddr, r);
+    tmem_ld16_issue(taddr + 16, r + 16);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-
 // ---- descriptors -------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -199,14 +200,15 @@ __device__ __forceinline__ void sh16(float x, float y, float z, float* e) {  // 
     e[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
 
-// hidden-layer epilogue: TMEM [128 x 64] fp32 -> relu -> fp16 -> next operand buffer (K = 64 layout)
-__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, uint8_t* dst, int row) {
-    float v[64];
-    tmem_ld64(tmem_row, v);
+// hidden-layer epilogue: TMEM [128 x 64] fp32 -> relu -> fp16 -> next operand buffer (K = 64 layout);
+// thread (row, hh) converts columns [32*hh, 32*hh+32) = chunks 4*hh .. 4*hh+3
+__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, uint8_t* dst, int row, int hh) {
+    float v[32];
+    tmem_ld32(tmem_row + hh * 32, v);
 #pragma unroll
-    for (int kc = 0; kc < 8; ++kc) {
+    for (int kc = 0; kc < 4; ++kc) {
         const float* q = v + kc * 8;
-        *reinterpret_cast<uint4*>(dst + chunk_off(row, kc, 64)) =
+        *reinterpret_cast<uint4*>(dst + chunk_off(row, hh * 4 + kc, 64)) =
             make_uint4(pack_h2(fmaxf(q[0], 0.f), fmaxf(q[1], 0.f)), pack_h2(fmaxf(q[2], 0.f), fmaxf(q[3], 0.f)),
                        pack_h2(fmaxf(q[4], 0.f), fmaxf(q[5], 0.f)), pack_h2(fmaxf(q[6], 0.f), fmaxf(q[7], 0.f)));
     }
@@ -215,33 +217,34 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, uint8_t* dst,
 // per-thread inputs of one tile row, fetched one tile ahead so the ~1 us DRAM latency overlaps the
 // previous tile's MMA / epilogue rounds
 struct RowIn {
-    uint4 e[4];          // 32 fp16 embedding values
-    float dx, dy, dz;
-    float dsig, dr[3];   // backward only
+    uint4 e[2];          // this thread's 2 of the row's 4 embedding chunks (16 fp16 values)
+    float dx, dy, dz;    // used by hh == 1 (SH)
+    float dsig, dr[3];   // backward only, used by hh == 0
 };
 template <typename TEmb, bool kBwd>
 __device__ __forceinline__ RowIn load_row(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
                                            const float* __restrict__ dsigmas, const __half* __restrict__ drgbs,
-                                           int64_t i, bool valid) {
+                                           int64_t i, bool valid, int hh) {
     RowIn r;
-#pragma unroll
-    for (int kc = 0; kc < 4; ++kc) r.e[kc] = make_uint4(0, 0, 0, 0);
+    r.e[0] = r.e[1] = make_uint4(0, 0, 0, 0);
     r.dx = 0.f; r.dy = 0.f; r.dz = 1.f; r.dsig = 0.f; r.dr[0] = r.dr[1] = r.dr[2] = 0.f;
     if (valid) {
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
+        for (int q = 0; q < 2; ++q) {
+            const int kc = hh * 2 + q;
             if constexpr (sizeof(TEmb) == 2) {
-                r.e[kc] = __ldg(reinterpret_cast<const uint4*>(emb + i * 32) + kc);
+                r.e[q] = __ldg(reinterpret_cast<const uint4*>(emb + i * 32) + kc);
             } else {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8));
                 const float4 b = __ldg(reinterpret_cast<const float4*>(emb + i * 32 + kc * 8 + 4));
-                r.e[kc] = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
+                r.e[q] = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
             }
         }
-        r.dx = __ldg(dirs + i * 3 + 0);
-        r.dy = __ldg(dirs + i * 3 + 1);
-        r.dz = __ldg(dirs + i * 3 + 2);
-        if constexpr (kBwd) {
+        if (hh == 1) {
+            r.dx = __ldg(dirs + i * 3 + 0);
+            r.dy = __ldg(dirs + i * 3 + 1);
+            r.dz = __ldg(dirs + i * 3 + 2);
+        } else if constexpr (kBwd) {
             r.dsig = __ldg(dsigmas + i);
 #pragma unroll
             for (int c = 0; c < 3; ++c) r.dr[c] = __half2float(drgbs[i * 3 + c]);
@@ -251,13 +254,13 @@ __device__ __forceinline__ RowIn load_row(const TEmb* __restrict__ emb, const fl
 }
 
 template <typename TEmb>
-__global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
+__global__ void __launch_bounds__(kThreads, 4) mlp_fwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
                                                            ngp_mlp_weights w, float* __restrict__ sigmas,
                                                            __half* __restrict__ rgbs, int64_t n_max,
                                                            const int32_t* __restrict__ n_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int64_t n = n_dev ? min(n_max, max((int64_t)*n_dev, (int64_t)0)) : n_max;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kRows - 1), hh = tid >> 7;
     const uint32_t bar = smem_u32(smem + kBar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBar + 8);
 
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restric
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's 32 lanes
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 lanes
     uint32_t phase = 0;
 
     const uint32_t aA = smem_u32(smem + kBufA), aB = smem_u32(smem + kBufB);
@@ -285,19 +288,19 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restric
                    aW4 = smem_u32(smem + kW4), aW5 = smem_u32(smem + kW5);
 
     const int64_t n_tiles = (n + kTile - 1) / kTile;
-    RowIn cur = load_row<TEmb, false>(emb, dirs, nullptr, nullptr, (int64_t)blockIdx.x * kTile + tid,
-                                      (int64_t)blockIdx.x * kTile + tid < n);
+    RowIn cur = load_row<TEmb, false>(emb, dirs, nullptr, nullptr, (int64_t)blockIdx.x * kTile + row,
+                                      (int64_t)blockIdx.x * kTile + row < n, hh);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = tile * kTile + tid;
+        const int64_t i = tile * kTile + row;
         const bool valid = i < n;
 
         // ---- stage X = emb[i, 0:32] as fp16 into bufA (K = 32 layout); inputs were fetched one tile ago
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(smem + kBufA + chunk_off(tid, kc, 32)) = cur.e[kc];
+        for (int q = 0; q < 2; ++q) *reinterpret_cast<uint4*>(smem + kBufA + chunk_off(row, hh * 2 + q, 32)) = cur.e[q];
         const float dx = cur.dx, dy = cur.dy, dz = cur.dz;
         {   // prefetch the next tile of this CTA
-            const int64_t in = (tile + gridDim.x) * kTile + tid;
-            cur = load_row<TEmb, false>(emb, dirs, nullptr, nullptr, in, in < n);
+            const int64_t in = (tile + gridDim.x) * kTile + row;
+            cur = load_row<TEmb, false>(emb, dirs, nullptr, nullptr, in, in < n, hh);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restric
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        epilogue_hidden(tmem_row, smem + kBufB, tid);
+        epilogue_hidden(tmem_row, smem + kBufB, row, hh);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -324,25 +327,27 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restric
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        {
+        if (hh == 0) {
+            // sigma = TruncExp(h[:,0]) (networks.py:22-24, :146) and the geometry half of X3 = [SH | h]
             float h[16];
             tmem_ld16(tmem_row, h);
-            // TruncExp forward on the fp16-rounded h[:,0] (networks.py:22-24, :146)
             const float h0 = __half2float(__float2half_rn(h[0]));
             if (valid) sigmas[i] = expf(h0);
-            // rgb-net input X3 = [SH16((d/|d| + 1)/2) | h]  (networks.py:162-164), K = 32 layout in bufA
+            uint8_t* dst = smem + kBufA;
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 2, 32)) =
+                make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 3, 32)) =
+                make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
+        } else {
+            // the direction half, in parallel: SH16((d/|d| + 1)/2)  (networks.py:162-164)
             const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
             float e[16];
             sh16((dx * inv + 1.0f) / 2.0f, (dy * inv + 1.0f) / 2.0f, (dz * inv + 1.0f) / 2.0f, e);
             uint8_t* dst = smem + kBufA;
-            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 0, 32)) =
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 0, 32)) =
                 make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
-            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 1, 32)) =
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 1, 32)) =
                 make_uint4(pack_h2(e[8], e[9]), pack_h2(e[10], e[11]), pack_h2(e[12], e[13]), pack_h2(e[14], e[15]));
-            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 2, 32)) =
-                make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
-            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 3, 32)) =
-                make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
         }
         fence_proxy_async();
         tc_fence_before();
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restric
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        epilogue_hidden(tmem_row, smem + kBufB, tid);
+        epilogue_hidden(tmem_row, smem + kBufB, row, hh);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restric
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        epilogue_hidden(tmem_row, smem + kBufA, tid);
+        epilogue_hidden(tmem_row, smem + kBufA, row, hh);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) mlp_fwd_kernel(const TEmb* __restric
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        {
+        if (hh == 0) {
             float o[16];
             tmem_ld16(tmem_row, o);
             if (valid) {
@@ -438,19 +443,20 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const Operand& a, co
 
 // backward hidden epilogue: TMEM [128 x 64] fp32 -> fp16, masked by relu'(act) where `act` holds the
 // post-ReLU forward activation of this thread's row -> dst (K = 64 layout).  dst may alias act.
-__device__ __forceinline__ void epilogue_relu_bwd(uint32_t tmem_row, const uint8_t* act, uint8_t* dst, int row) {
-    float v[64];
-    tmem_ld64(tmem_row, v);
+__device__ __forceinline__ void epilogue_relu_bwd(uint32_t tmem_row, const uint8_t* act, uint8_t* dst, int row, int hh) {
+    float v[32];
+    tmem_ld32(tmem_row + hh * 32, v);
 #pragma unroll
-    for (int kc = 0; kc < 8; ++kc) {
+    for (int q = 0; q < 4; ++q) {
+        const int kc = hh * 4 + q;
         const uint4 a = *reinterpret_cast<const uint4*>(act + chunk_off(row, kc, 64));
         const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const __half2 ah = *reinterpret_cast<const __half2*>(&aw[j]);
-            const float m0 = __low2float(ah) > 0.0f ? v[kc * 8 + 2 * j] : 0.0f;
-            const float m1 = __high2float(ah) > 0.0f ? v[kc * 8 + 2 * j + 1] : 0.0f;
+            const float m0 = __low2float(ah) > 0.0f ? v[q * 8 + 2 * j] : 0.0f;
+            const float m1 = __high2float(ah) > 0.0f ? v[q * 8 + 2 * j + 1] : 0.0f;
             o[j] = pack_h2(m0, m1);
         }
         *reinterpret_cast<uint4*>(dst + chunk_off(row, kc, 64)) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -458,14 +464,14 @@ __device__ __forceinline__ void epilogue_relu_bwd(uint32_t tmem_row, const uint8
 }
 
 template <typename TEmb>
-__global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
+__global__ void __launch_bounds__(kThreads, 2) mlp_bwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
                                                            ngp_mlp_weights w, const float* __restrict__ dsigmas,
                                                            const __half* __restrict__ drgbs, TEmb* __restrict__ demb,
                                                            float* __restrict__ grad_w, int64_t n_max,
                                                            const int32_t* __restrict__ n_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int64_t n = n_dev ? min(n_max, max((int64_t)*n_dev, (int64_t)0)) : n_max;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & (kRows - 1), hh = tid >> 7;
     const uint32_t bar = smem_u32(smem + kBarBwd);
     const uint32_t bar2 = smem_u32(smem + kBarBwd + 16);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBarBwd + 8);
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t phase = 0;
 
     const uint32_t aW1 = smem_u32(smem + kW1), aW2 = smem_u32(smem + kW2), aW3 = smem_u32(smem + kW3),
@@ -518,48 +524,50 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
 
     bool first = true;  // first tile of this CTA: weight-gradient accumulators start from zero
     const int64_t n_tiles = (n + kTile - 1) / kTile;
-    RowIn cur = load_row<TEmb, true>(emb, dirs, dsigmas, drgbs, (int64_t)blockIdx.x * kTile + tid,
-                                     (int64_t)blockIdx.x * kTile + tid < n);
+    RowIn cur = load_row<TEmb, true>(emb, dirs, dsigmas, drgbs, (int64_t)blockIdx.x * kTile + row,
+                                     (int64_t)blockIdx.x * kTile + row < n, hh);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = tile * kTile + tid;
+        const int64_t i = tile * kTile + row;
         const bool valid = i < n;
 
         // ================= forward recompute =================
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(smem + kE + chunk_off(tid, kc, 32)) = cur.e[kc];
-        const float dx = cur.dx, dy = cur.dy, dz = cur.dz, dsig = cur.dsig;
+        for (int q = 0; q < 2; ++q) *reinterpret_cast<uint4*>(smem + kE + chunk_off(row, hh * 2 + q, 32)) = cur.e[q];
+        const float dx = cur.dx, dy = cur.dy, dz = cur.dz, dsig = cur.dsig;  // dirs: hh == 1, dsig/dr: hh == 0
         const float dr[3] = {cur.dr[0], cur.dr[1], cur.dr[2]};
         {   // prefetch the next tile of this CTA (consumed one iteration later)
-            const int64_t in = (tile + gridDim.x) * kTile + tid;
-            cur = load_row<TEmb, true>(emb, dirs, dsigmas, drgbs, in, in < n);
+            const int64_t in = (tile + gridDim.x) * kTile + row;
+            cur = load_row<TEmb, true>(emb, dirs, dsigmas, drgbs, in, in < n, hh);
         }
         NGP_ROUND(issue_layer_mma(tmem_base, aE, aW1, 32, 64))          // H1 = relu(E W1^T)
-        epilogue_hidden(tmem_row, smem + kH1, tid);
+        epilogue_hidden(tmem_row, smem + kH1, row, hh);
         NGP_ROUND(issue_layer_mma(tmem_base, aH1, aW2, 64, 16))         // h = H1 W2^T
-        float h0;
-        {
+        float h0 = 0.0f;
+        if (hh == 0) {
             float h[16];
             tmem_ld16(tmem_row, h);
             h0 = __half2float(__float2half_rn(h[0]));
+            uint8_t* dst = smem + kX3;
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 2, 32)) =
+                make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 3, 32)) =
+                make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
+        } else {
             const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
             float e[16];
             sh16((dx * inv + 1.0f) / 2.0f, (dy * inv + 1.0f) / 2.0f, (dz * inv + 1.0f) / 2.0f, e);
             uint8_t* dst = smem + kX3;
-            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 0, 32)) =
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 0, 32)) =
                 make_uint4(pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
-            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 1, 32)) =
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 1, 32)) =
                 make_uint4(pack_h2(e[8], e[9]), pack_h2(e[10], e[11]), pack_h2(e[12], e[13]), pack_h2(e[14], e[15]));
-            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 2, 32)) =
-                make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
-            *reinterpret_cast<uint4*>(dst + chunk_off(tid, 3, 32)) =
-                make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
         }
         NGP_ROUND(issue_layer_mma(tmem_base, aX3, aW3, 32, 64))         // H3 = relu(X3 W3^T)
-        epilogue_hidden(tmem_row, smem + kH3, tid);
+        epilogue_hidden(tmem_row, smem + kH3, row, hh);
         NGP_ROUND(issue_layer_mma(tmem_base, aH3, aW4, 64, 64))         // H4 = relu(H3 W4^T)
-        epilogue_hidden(tmem_row, smem + kH4, tid);
+        epilogue_hidden(tmem_row, smem + kH4, row, hh);
         NGP_ROUND(issue_layer_mma(tmem_base, aH4, aW5, 64, 16))         // o = H4 W5^T
-        {
+        if (hh == 0) {
             // dL/do = dL/drgb * rgb (1 - rgb), rounded to fp16 like the autocast graph
             float o[16];
             tmem_ld16(tmem_row, o);
@@ -570,9 +578,10 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
                 const float rgb = __half2float(__float2half_rn(1.0f / (1.0f + expf(-oc))));
                 d_o[c] = dr[c] * rgb * (1.0f - rgb);
             }
-            *reinterpret_cast<uint4*>(smem + kDO + chunk_off(tid, 0, 16)) =
+            *reinterpret_cast<uint4*>(smem + kDO + chunk_off(row, 0, 16)) =
                 make_uint4(pack_h2(d_o[0], d_o[1]), pack_h2(d_o[2], 0.0f), 0u, 0u);
-            *reinterpret_cast<uint4*>(smem + kDO + chunk_off(tid, 1, 16)) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            *reinterpret_cast<uint4*>(smem + kDO + chunk_off(row, 1, 16)) = make_uint4(0u, 0u, 0u, 0u);
         }
 
         // ================= backward =================
@@ -581,27 +590,27 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
             issue_gemm(tmem_base, op_kmajor(aDO, 16), op_mnmajor(aW5, 64), 1, idesc_full(128, 64, 0, 1), false),
             issue_gemm(tmem_base + kColDW5T, op_mnmajor(aH4, 64), op_mnmajor(aDO, 16), 8, idesc_full(64, 16, 1, 1), !first),
             false)
-        epilogue_relu_bwd(tmem_row, smem + kH4, smem + kDH4, tid);
+        epilogue_relu_bwd(tmem_row, smem + kH4, smem + kDH4, row, hh);
         // R2: dH3pre = dH4 W4 ;  dW4 += dH4^T H3
         NGP_ROUND2(
             issue_gemm(tmem_base, op_kmajor(aDH4, 64), op_mnmajor(aW4, 64), 4, idesc_full(128, 64, 0, 1), false),
             issue_gemm(tmem_base + kColDW4, op_mnmajor(aDH4, 64), op_mnmajor(aH3, 64), 8, idesc_full(64, 64, 1, 1), !first),
             false)
-        epilogue_relu_bwd(tmem_row, smem + kH3, smem + kH4, tid);      // dH3 -> H4's buffer (H4 is dead)
+        epilogue_relu_bwd(tmem_row, smem + kH3, smem + kH4, row, hh);      // dH3 -> H4's buffer (H4 is dead)
         // R3: dX3 = dH3 W3 ;  dW3 += dH3^T X3
         NGP_ROUND2(
             issue_gemm(tmem_base, op_kmajor(aH4, 64), op_mnmajor(aW3, 32), 4, idesc_full(128, 32, 0, 1), false),
             issue_gemm(tmem_base + kColDW3, op_mnmajor(aH4, 64), op_mnmajor(aX3, 32), 8, idesc_full(64, 32, 1, 1), !first),
             false)
-        {
+        if (hh == 0) {
             // dh = dX3[:, 16:32] (+ TruncExp backward on h[:,0], networks.py:26-30), fp16
             float g[16];
             tmem_ld16(tmem_row + 16, g);
             const float ds = __half2float(__float2half_rn(dsig * expf(fminf(fmaxf(h0, -15.0f), 15.0f))));
             g[0] = __half2float(__float2half_rn(g[0])) + ds;
-            *reinterpret_cast<uint4*>(smem + kDH + chunk_off(tid, 0, 16)) =
+            *reinterpret_cast<uint4*>(smem + kDH + chunk_off(row, 0, 16)) =
                 make_uint4(pack_h2(g[0], g[1]), pack_h2(g[2], g[3]), pack_h2(g[4], g[5]), pack_h2(g[6], g[7]));
-            *reinterpret_cast<uint4*>(smem + kDH + chunk_off(tid, 1, 16)) =
+            *reinterpret_cast<uint4*>(smem + kDH + chunk_off(row, 1, 16)) =
                 make_uint4(pack_h2(g[8], g[9]), pack_h2(g[10], g[11]), pack_h2(g[12], g[13]), pack_h2(g[14], g[15]));
         }
         // R4: dH1pre = dh W2 ;  dW2^T += H1^T dh
@@ -609,29 +618,27 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
             issue_gemm(tmem_base, op_kmajor(aDH, 16), op_mnmajor(aW2, 64), 1, idesc_full(128, 64, 0, 1), false),
             issue_gemm(tmem_base + kColDW2T, op_mnmajor(aH1, 64), op_mnmajor(aDH, 16), 8, idesc_full(64, 16, 1, 1), !first),
             false)
-        epilogue_relu_bwd(tmem_row, smem + kH1, smem + kH3, tid);      // dH1 -> H3's buffer (H3 is dead)
+        epilogue_relu_bwd(tmem_row, smem + kH1, smem + kH3, row, hh);      // dH1 -> H3's buffer (H3 is dead)
         // R5: dE = dH1 W1 ;  dW1 += dH1^T E
         NGP_ROUND2(
             issue_gemm(tmem_base, op_kmajor(aH3, 64), op_mnmajor(aW1, 32), 4, idesc_full(128, 32, 0, 1), false),
             issue_gemm(tmem_base + kColDW1, op_mnmajor(aH3, 64), op_mnmajor(aE, 32), 8, idesc_full(64, 32, 1, 1), !first),
             true)
         {
+            const int g = hh;  // columns [16*hh, 16*hh+16) of dE
+            float v[16];
+            tmem_ld16(tmem_row + g * 16, v);
+            if (valid) {
+                if constexpr (sizeof(TEmb) == 2) {
+                    uint4* o = reinterpret_cast<uint4*>(demb + i * 32 + g * 16);
+                    o[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                    o[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+                } else {
+                    float4* o = reinterpret_cast<float4*>(demb + i * 32 + g * 16);
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                float v[16];
-                tmem_ld16(tmem_row + g * 16, v);
-                if (valid) {
-                    if constexpr (sizeof(TEmb) == 2) {
-                        uint4* o = reinterpret_cast<uint4*>(demb + i * 32 + g * 16);
-                        o[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-                        o[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
-                    } else {
-                        float4* o = reinterpret_cast<float4*>(demb + i * 32 + g * 16);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {  // fp16-rounded like the autocast graph, stored as fp32
-                            o[q] = make_float4(__half2float(__float2half_rn(v[4 * q])), __half2float(__float2half_rn(v[4 * q + 1])),
-                                               __half2float(__float2half_rn(v[4 * q + 2])), __half2float(__float2half_rn(v[4 * q + 3])));
-                        }
+                    for (int q = 0; q < 4; ++q) {  // fp16-rounded like the autocast graph, stored as fp32
+                        o[q] = make_float4(__half2float(__float2half_rn(v[4 * q])), __half2float(__float2half_rn(v[4 * q + 1])),
+                                           __half2float(__float2half_rn(v[4 * q + 2])), __half2float(__float2half_rn(v[4 * q + 3])));
                     }
                 }
             }
@@ -646,7 +653,7 @@ __global__ void __launch_bounds__(kThreads) mlp_bwd_kernel(const TEmb* __restric
 #undef NGP_ROUND2
 
     // ---- flush the weight-gradient accumulators: M = 64 rows live on TMEM lanes (m%16) + 32*(m/16)
-    if (!first) {
+    if (!first && warp < 4) {
         const int m = warp * 16 + lane;  // row held by this thread when lane < 16
         const bool has_row = lane < 16;
         float v[16];
