@@ -166,13 +166,22 @@ def run_ours(args):
     sample_counts = []
     from taichi_nerfs_b200.fast_step import StaticTrainStep
     fast = None if args.path == "modules" else StaticTrainStep(trainer, BATCH, samples_per_ray_capacity=384)
+    if fast is not None:
+        # the training set stays resident in HBM (train.py: `train_dataset.to(device)`), and the step draws its own
+        # batch on the device (datasets/base.py:34-61 + get_rays as the first node of the graph)
+        ds.build_image_bank()
+        fast.attach_ray_source(ds.rays, ds.poses, ds.directions, seed=SEED + rank)
 
     def one_step(step_idx, b):
         with torch.autocast("cuda", dtype=torch.float16):
             if step_idx % UPDATE_INTERVAL == 0:
                 model.update_density_grid(DENSITY_THRESHOLD, warmup=step_idx < 256)
+        if fast is not None and b is None:   # batch sampling + the whole step = one CUDA-graph replay, no host sync
+            loss = fast.step_sampled()
+            sample_counts.append(fast.counter[0].clone())
+            return loss
         rays_o, rays_d = get_rays(b["direction"], b["pose"])
-        if fast is not None:   # the whole step is one CUDA-graph replay, no host sync
+        if fast is not None:   # caller-provided batch (host buffers in the e2e arm)
             loss = fast.step(rays_o, rays_d, b["rgb"])
             sample_counts.append(fast.counter[0].clone())
         else:                  # reference-shaped module API: render() + autograd + fused Adam
@@ -197,6 +206,8 @@ def run_ours(args):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms)
 
+    if fast is not None:
+        batches = [None] * n_total   # "value" arm: batches are drawn on the device inside the graph
     if args.ncu_window > 0:
         for s in range(PREWARM):
             one_step(1 + s % 8, batches[s % len(batches)])
@@ -220,11 +231,13 @@ def run_ours(args):
         one_step(s, batches[s])
     launches0 = _lib.launch_count()
     replays0 = fast.replays if fast is not None else 0
+    sampled0 = fast.replays_sampled if fast is not None else 0
     ms_total = timed(lambda: [one_step(args.warmup + k, batches[args.warmup + k]) for k in range(args.steps)])
     clock_info = clocks.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0   # eager launches of libngp_b200 kernels
     if fast is not None:                          # + kernel nodes executed by CUDA-graph replays
         launches += (fast.replays - replays0) * fast.kernels_per_replay
+        launches += (fast.replays_sampled - sampled0) * fast.kernels_per_replay_sampled
     ms_step = ms_total / args.steps
     value = world * BATCH / (ms_step * 1e-3)
     spr = float(torch.stack([c.float() for c in sample_counts[-args.steps:]]).mean()) / BATCH
@@ -267,7 +280,9 @@ def run_ours(args):
                    "density_grid_update": f"inside timed loop every {UPDATE_INTERVAL} steps (warm-up mode); "
                                           f"{upd_ms:.3f} ms each",
                    "mlp": "torch.nn.Linear (cuBLAS) under autocast" if not _fused_mlp() else "fused tcgen05 kernel",
-                   "step_path": "StaticTrainStep: whole step = one CUDA-graph replay, sample count stays on the device"
+                   "step_path": "StaticTrainStep: batch sampling (resident 100x800x800 training set) + whole step = one "
+                                "CUDA-graph replay, sample count stays on the device; e2e arm: host batches -> get_rays -> "
+                                "the same graph without the sampler node"
                                 if fast is not None else "modules API: render() + torch.autograd + fused Adam"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),

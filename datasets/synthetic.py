@@ -80,6 +80,7 @@ class SyntheticLego:
         self.directions = get_ray_directions(h, w, self.K)
         self.poses = hemisphere_poses(n_images, radius, seed)
         self._gen = None
+        self.rays = None
         self._seed = seed
         self.with_rgb = with_rgb
 
@@ -90,7 +91,27 @@ class SyntheticLego:
         self.K = self.K.to(device)
         self.directions = self.directions.to(device)
         self.poses = self.poses.to(device)
+        if self.rays is not None:
+            self.rays = self.rays.to(device)
         return self
+
+    def build_image_bank(self):
+        """``self.rays`` [n_images, H*W, 3]: every training pixel resident, as the reference's datasets keep them
+        (datasets/nsvf.py / colmap.py ``self.rays``; moved to the GPU by BaseDataset.to, base.py:26-31).  Needed by
+        the on-device batch sampler (ngp_sample_ray_batch / StaticTrainStep.attach_ray_source)."""
+        dev = self.poses.device
+        n_pix = self.img_wh[0] * self.img_wh[1]
+        if self.scene == 'analytic':
+            from .ray_utils import get_rays
+            imgs = []
+            for pose in self.poses:
+                o, d = get_rays(self.directions, pose)
+                imgs.append(torch.cat([render_teacher(o[i:i + 65536], d[i:i + 65536]) for i in range(0, n_pix, 65536)]))
+            self.rays = torch.stack(imgs)
+        else:
+            g = torch.Generator(device=dev).manual_seed(self._seed + 7)
+            self.rays = torch.rand(len(self.poses), n_pix, 3, device=dev, generator=g)
+        return self.rays
 
     def __getitem__(self, idx):
         dev = self.poses.device

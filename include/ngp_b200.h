@@ -267,6 +267,26 @@ int ngp_packbits_dev(const float* density_grid, const float* mean_density_dev, f
 int ngp_morton3d(const int32_t* coords, int32_t* indices, int64_t n, void* stream);
 int ngp_morton3d_invert(const int32_t* indices, int32_t* coords, int64_t n, void* stream);
 
+/* ---- training ray batch sampling ------------------------ */
+/* replaces, per step: BaseDataset.__getitem__ (datasets/base.py:34-61: torch.randint x2 + gathers of
+ * self.rays / self.poses / self.directions), get_rays (datasets/ray_utils.py:51-80:
+ * rays_d = directions @ c2w[:, :3].T, rays_o = c2w[:, 3]) and the per-ray marching jitter
+ * torch.rand_like (modules/ray_march.py:166), in one launch.
+ *   image_bank [n_img, n_pix, channels] f32 (channels >= 3; may be NULL when rgb == NULL)
+ *   poses [n_img, 3, 4] f32, directions [n_pix, 3] f32 (get_ray_directions, ray_utils.py:8-48)
+ *   img_idxs / pix_idxs [n_rays] int64: the reference's sample['img_idxs'/'pix_idxs']; when NULL the
+ *     index is drawn from Philox4x32-10 with counter (ray, ray>>32, step, 0) and key = seed:
+ *     img = (r0 * n_img) >> 32 (or fixed_img when >= 0: ray_sampling_strategy 'same_image'),
+ *     pix = (r1 * n_pix) >> 32, noise = (r2 >> 8) * 2^-24
+ *   step: *step_dev when step_dev != NULL (CUDA-graph replayable), else step_host
+ *   outputs rays_o / rays_d / rgb [n_rays, 3] f32, noise [n_rays] f32 (NULL = skip),
+ *   img_out / pix_out [n_rays] int64 (NULL = skip) */
+int ngp_sample_ray_batch(const float* image_bank, int channels, const float* poses, const float* directions,
+                         int64_t n_img, int64_t n_pix, const int64_t* img_idxs, const int64_t* pix_idxs,
+                         int64_t fixed_img, uint64_t seed, const int32_t* step_dev, int32_t step_host,
+                         float* rays_o, float* rays_d, float* rgb, float* noise, int64_t* img_out,
+                         int64_t* pix_out, int64_t n_rays, void* stream);
+
 /* ---- a12: fused optimizer pass ---------------------------------------------- */
 /* replaces GradScaler.unscale_ + inf check + torch.optim.Adam(eps=1e-15) step
  * (train.py:137-156,197-201) in ONE pass over the parameters:

@@ -946,3 +946,58 @@ int ngp_adam_step_cpu(float* param, float* grad, float* exp_avg, float* exp_avg_
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* training ray batch sampling   datasets/base.py:34-61, ray_utils.py:51-80   */
+/* ------------------------------------------------------------------------- */
+/* Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11;
+ * the generator behind torch's CUDA randint/rand).  Pinned against the Random123 known-answer
+ * vectors in tests/test_oracle.py. */
+void ngp_philox4x32_10_cpu(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0;
+        c1 = (uint32_t)p1;
+        c2 = n2;
+        c3 = (uint32_t)p0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* The reference draws img/pix with torch.randint (base.py:38-52), gathers rays/poses/directions
+ * (:53-60) and rotates directions by the pose (ray_utils.py:67-75); the index draw here is the
+ * library's own Philox mapping (documented in include/ngp_b200.h), the rest follows the reference. */
+int ngp_sample_ray_batch_cpu(const float* image_bank, int channels, const float* poses, const float* directions,
+                             int64_t n_img, int64_t n_pix, const int64_t* img_idxs, const int64_t* pix_idxs,
+                             int64_t fixed_img, uint64_t seed, int32_t step, float* rays_o, float* rays_d,
+                             float* rgb, float* noise, int64_t* img_out, int64_t* pix_out, int64_t n_rays) {
+    for (int64_t i = 0; i < n_rays; ++i) {
+        const uint32_t ctr[4] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)step, 0u};
+        const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        uint32_t r[4];
+        ngp_philox4x32_10_cpu(ctr, key, r);
+        int64_t img = img_idxs ? img_idxs[i]
+                               : (fixed_img >= 0 ? fixed_img : (int64_t)(((uint64_t)r[0] * (uint64_t)n_img) >> 32));
+        int64_t pix = pix_idxs ? pix_idxs[i] : (int64_t)(((uint64_t)r[1] * (uint64_t)n_pix) >> 32);
+        if (img < 0) img = 0;
+        if (img > n_img - 1) img = n_img - 1;
+        if (pix < 0) pix = 0;
+        if (pix > n_pix - 1) pix = n_pix - 1;
+        const float* P = poses + img * 12;
+        const float* d = directions + pix * 3;
+        for (int a = 0; a < 3; ++a) {
+            rays_d[i * 3 + a] = (d[0] * P[a * 4 + 0] + d[1] * P[a * 4 + 1]) + d[2] * P[a * 4 + 2];
+            rays_o[i * 3 + a] = P[a * 4 + 3];
+        }
+        if (rgb)
+            for (int c = 0; c < 3; ++c) rgb[i * 3 + c] = image_bank[(img * n_pix + pix) * channels + c];
+        if (noise) noise[i] = (float)(r[2] >> 8) * 5.9604644775390625e-8f;
+        if (img_out) img_out[i] = img;
+        if (pix_out) pix_out[i] = pix;
+    }
+    return 0;
+}

@@ -296,3 +296,30 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999
                                  C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                                  C.c_float(inv_scale), C.c_int32(step), C.c_int(int(zero_grad)),
                                  C.c_int64(param.size)))
+
+
+def philox4x32_10(ctr, key):
+    c, k = _c(ctr, np.uint32), _c(key, np.uint32)
+    out = np.empty(4, np.uint32)
+    lib().ngp_philox4x32_10_cpu(_p(c), _p(k), _p(out))
+    return out
+
+
+def sample_ray_batch(image_bank, poses, directions, n_rays, img_idxs=None, pix_idxs=None, fixed_img=-1, seed=0,
+                     step=0):
+    """datasets/base.py:34-61 + datasets/ray_utils.py:51-80 (+ the marching jitter) for one batch."""
+    bank = None if image_bank is None else _c(image_bank, np.float32)
+    P, D = _c(poses, np.float32), _c(directions, np.float32)
+    ii = None if img_idxs is None else _c(img_idxs, np.int64)
+    pi = None if pix_idxs is None else _c(pix_idxs, np.int64)
+    o, d = np.empty((n_rays, 3), np.float32), np.empty((n_rays, 3), np.float32)
+    rgb = None if bank is None else np.empty((n_rays, 3), np.float32)
+    noise = np.empty(n_rays, np.float32)
+    io, po = np.empty(n_rays, np.int64), np.empty(n_rays, np.int64)
+    n = lambda a: None if a is None else _p(a)  # noqa: E731
+    lib().ngp_sample_ray_batch_cpu.restype = C.c_int
+    _chk(lib().ngp_sample_ray_batch_cpu(n(bank), C.c_int(0 if bank is None else bank.shape[2]), _p(P), _p(D),
+                                        C.c_int64(P.shape[0]), C.c_int64(D.shape[0]), n(ii), n(pi),
+                                        C.c_int64(fixed_img), C.c_uint64(seed), C.c_int32(step), _p(o), _p(d), n(rgb),
+                                        _p(noise), _p(io), _p(po), C.c_int64(n_rays)))
+    return {"rays_o": o, "rays_d": d, "rgb": rgb, "noise": noise, "img_idxs": io, "pix_idxs": po}

@@ -66,6 +66,8 @@ def _declare(lib):
         "ngp_distortion_bwd": (ci, [vp, vp, vp, vp, vp, vp, i64, i64, vp]),
         "ngp_packbits": (ci, [vp, f32, vp, i64, vp]),
         "ngp_packbits_dev": (ci, [vp, vp, f32, vp, i64, vp]),
+        "ngp_sample_ray_batch": (ci, [vp, ci, vp, vp, i64, i64, vp, vp, i64, C.c_uint64, vp, i32,
+                                      vp, vp, vp, vp, vp, vp, i64, vp]),
         "ngp_morton3d": (ci, [vp, vp, i64, vp]),
         "ngp_morton3d_invert": (ci, [vp, vp, i64, vp]),
         "ngp_adam_step": (ci, [vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, ci, i64, vp]),

@@ -3,9 +3,10 @@
 Same math as NGPTrainer.step / the reference's loop body (train.py:184-201) — every stage is one of
 the C-ABI kernels, enqueued in a fixed order on fixed buffers:
 
-  ray_aabb -> march count/scan/write (capacity buffers) -> hash fwd (+AABB normalisation) -> tcgen05 MLP
-  fwd -> composite fwd -> loss head (MSE + bg) -> composite bwd -> MLP bwd -> hash bwd -> [all-reduce]
-  -> check_finite -> device-side LR/bias-correction update -> fused Adam (+fp16 shadow, grad zero)
+  [ray-batch sampler] -> ray_aabb -> single-pass march (capacity buffers, one atomic row reservation per ray) ->
+  hash fwd (+AABB normalisation) -> tcgen05 MLP fwd -> fused per-ray head (composite fwd + background + MSE +
+  composite bwd) -> MLP bwd -> hash bwd -> [all-reduce] -> check_finite -> device-side LR/bias-correction update
+  -> fused Adam (+fp16 shadow, grad zero) -> device-side GradScaler update
 
 What makes it graph-capturable: the number of samples S stays on the device (kernels read it from the
 march counter; buffers are sized for `capacity` rows and rays that would overflow are dropped and
@@ -79,12 +80,17 @@ class StaticTrainStep:
         jitter = (torch.arange(self.n, device=dev, dtype=f32)[:, None] % 97) * 1e-3
         self.rays_d[:] = -self.rays_o + jitter * torch.tensor([0.3, -0.2, 0.1], device=dev)
         self.graph = None
+        self.graph_sampled = None      # second graph with the ray-batch sampler as its first node
+        self.src = None
         self.kernels_per_replay = 0
+        self.kernels_per_replay_sampled = 0
         self.replays = 0
+        self.replays_sampled = 0
         self.use_graph = bool(use_graph)
         if self.use_graph:
             try:
-                self._capture()  # with world_size > 1 the NCCL all-reduce is captured as a graph node too
+                # with world_size > 1 the NCCL all-reduce is captured as a graph node too
+                self.graph, self.kernels_per_replay = self._capture(sampled=False)
             except RuntimeError as e:  # pragma: no cover - depends on the NCCL / driver combination
                 if parallel.world_info(trainer.pg)[1] == 1:
                     raise
@@ -150,13 +156,23 @@ class StaticTrainStep:
             check(L.ngp_loss_scale_update(_p(self.scale_state), _p(tr.found_inf), 2.0, 0.5, 2000, float(tr.world_size),
                                           _p(self.hyper), st))
 
-    def _enqueue(self):
+    def _enqueue_sampler(self):
+        """datasets/base.py:34-61 + ray_utils.py:51-80 + the marching jitter, keyed by (seed, step_dev, ray)."""
+        src = self.src
+        check(load().ngp_sample_ray_batch(_p(src["bank"]), src["bank"].shape[2], _p(src["poses"]), _p(src["dirs"]),
+                                          src["poses"].shape[0], src["dirs"].shape[0], None, None, src["fixed_img"],
+                                          src["seed"], _p(self.step_dev), 0, _p(self.rays_o), _p(self.rays_d),
+                                          _p(self.gt), _p(self.noise), None, None, self.n, self._st()))
+
+    def _enqueue(self, sampled=False):
+        if sampled:
+            self._enqueue_sampler()
         self._enqueue_forward_backward()
         if self.tr.world_size > 1:
             parallel.allreduce_gradients(self.tr.flat_grad, self.tr.pg)
         self._enqueue_optimizer()
 
-    def _capture(self):
+    def _capture(self, sampled):
         # the graph must not mutate training state while being built: snapshot, warm up + capture, restore
         tr = self.tr
         keep = [p.data.clone() for p in tr.params] + [tr.exp_avg.clone(), tr.exp_avg_sq.clone(), self.step_dev.clone()]
@@ -166,14 +182,14 @@ class StaticTrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                self._enqueue()
+                self._enqueue(sampled)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
-            self._enqueue()
-        self.kernels_per_replay = _lib.launch_count() - before  # libngp_b200 kernel nodes in the graph
+        with torch.cuda.graph(graph):
+            self._enqueue(sampled)
+        kernels = _lib.launch_count() - before  # libngp_b200 kernel nodes in the graph
         torch.cuda.synchronize()
         for p, k in zip(tr.params, keep):
             p.data.copy_(k)
@@ -185,6 +201,7 @@ class StaticTrainStep:
         tr.flat_grad.zero_()
         if shadow is not None:
             tr._shadow.copy_(shadow)
+        return graph, kernels
 
     # ---------------------------------------------------------------------------------------------
     def step(self, rays_o, rays_d, rgb_gt, noise=None):
@@ -201,11 +218,39 @@ class StaticTrainStep:
             self.replays += 1
         else:
             self._enqueue()
+        return self._finish_step()
+
+    def _finish_step(self):
         self.tr.step_count += 1
         enc = self.model.pos_encoder
         if self.tr._shadow is not None:
             enc.adopt_shadow(self.tr._shadow)
         return self.loss_sum / (3.0 * self.n)
+
+    def attach_ray_source(self, image_bank, poses, directions, seed: int = 0, fixed_img: int = -1):
+        """Keep the training set resident (as the reference's ``train_dataset.to(device)``) and let the step draw
+        its own batch: ``step_sampled()`` then needs no per-step input at all.  With several ranks pass a
+        different ``seed`` per rank."""
+        f = lambda t: t.detach().to(self.dev, torch.float32).contiguous()  # noqa: E731
+        bank, poses, directions = f(image_bank), f(poses), f(directions)
+        if bank.ndim != 3 or bank.shape[0] != poses.shape[0] or bank.shape[1] != directions.shape[0] or bank.shape[2] < 3:
+            raise ValueError(f"image bank {tuple(bank.shape)} vs {poses.shape[0]} poses x {directions.shape[0]} pixels")
+        self.src = dict(bank=bank, poses=poses.reshape(-1, 3, 4), dirs=directions, seed=int(seed),
+                        fixed_img=int(fixed_img))
+        if self.use_graph:
+            self.graph_sampled, self.kernels_per_replay_sampled = self._capture(sampled=True)
+        return self
+
+    def step_sampled(self):
+        """One training step on a batch drawn on the device (no host input, no host sync)."""
+        if self.src is None:
+            raise _lib.NgpError("step_sampled() needs attach_ray_source() first")
+        if self.graph_sampled is not None:
+            self.graph_sampled.replay()
+            self.replays_sampled += 1
+        else:
+            self._enqueue(sampled=True)
+        return self._finish_step()
 
     def stats(self):
         """(samples marched, rays) of the LAST enqueued step — device tensors, no sync."""

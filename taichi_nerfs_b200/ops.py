@@ -209,6 +209,38 @@ def packbits(density_grid, threshold, bitfield, mean_dev=None):
                                       bitfield.shape[0], _stream()), "packbits_dev")
 
 
+def sample_ray_batch(image_bank, poses, directions, n_rays, *, img_idxs=None, pix_idxs=None, fixed_img=-1, seed=0,
+                     step=0, step_dev=None, with_noise=True, return_indices=False, out=None):
+    """One launch for BaseDataset.__getitem__ + get_rays + the marching jitter (include/ngp_b200.h,
+    ngp_sample_ray_batch).  ``out`` = optional dict of preallocated rays_o / rays_d / rgb / noise (graph capture)."""
+    _need_cuda(poses, directions)
+    dev = poses.device
+    bank = None if image_bank is None else _f32c(image_bank)
+    poses, directions = _f32c(poses), _f32c(directions)
+    n_img, n_pix = poses.shape[0], directions.shape[0]
+    if bank is not None and tuple(bank.shape[:2]) != (n_img, n_pix):
+        raise ValueError(f"image bank {tuple(bank.shape)} does not match {n_img} poses x {n_pix} pixels")
+    out = {} if out is None else out
+    f = lambda k, *s: out[k] if k in out else torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+    rays_o, rays_d = f("rays_o", n_rays, 3), f("rays_d", n_rays, 3)
+    rgb = None if bank is None else f("rgb", n_rays, 3)
+    noise = f("noise", n_rays) if with_noise else None
+    ii = pi = None
+    if return_indices:
+        ii = torch.empty(n_rays, device=dev, dtype=torch.int64)
+        pi = torch.empty(n_rays, device=dev, dtype=torch.int64)
+    img_in = None if img_idxs is None else img_idxs.to(torch.int64).contiguous()
+    pix_in = None if pix_idxs is None else pix_idxs.to(torch.int64).contiguous()
+    check(load().ngp_sample_ray_batch(_ptr(bank), 0 if bank is None else bank.shape[2], _ptr(poses), _ptr(directions),
+                                      n_img, n_pix, _ptr(img_in), _ptr(pix_in), int(fixed_img), int(seed),
+                                      _ptr(step_dev), int(step), _ptr(rays_o), _ptr(rays_d), _ptr(rgb), _ptr(noise),
+                                      _ptr(ii), _ptr(pi), n_rays, _stream()), "sample_ray_batch")
+    res = {"rays_o": rays_o, "rays_d": rays_d, "rgb": rgb, "noise": noise}
+    if return_indices:
+        res["img_idxs"], res["pix_idxs"] = ii, pi
+    return res
+
+
 def morton3d(coords):
     _need_cuda(coords)
     c = coords.contiguous()

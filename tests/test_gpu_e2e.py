@@ -225,3 +225,46 @@ def test_device_side_grad_scaler(lego_bitfield):
     fs.step(o, d, torch.rand(n, 3, device='cuda'))                      # training continues with the halved scale
     assert all(torch.isfinite(p).all() for p in m.parameters())
     assert any(not torch.equal(p, b) for p, b in zip(m.parameters(), before))
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_static_step_with_device_sampled_batches(lego_bitfield, use_graph):
+    """step_sampled() (batch drawn inside the graph from the resident training set) == step() fed with the
+    oracle's restatement of the same draw, for three consecutive steps (the draw depends on the device step)."""
+    from datasets.synthetic import SyntheticLego
+    from modules.networks import NGP
+    from oracle import oracle as O
+    from taichi_nerfs_b200.fast_step import StaticTrainStep
+    from taichi_nerfs_b200.trainer import NGPTrainer
+
+    ds = SyntheticLego(n_images=6, img_wh=(64, 64), focal=88.9, batch_size=1024, seed=2).to('cuda')
+    ds.build_image_bank()
+
+    def build():
+        torch.manual_seed(3)
+        m = NGP(scale=0.5, max_res=1024, half_opt=True).cuda()
+        with torch.no_grad():
+            m.pos_encoder.hash_table.mul_(2e3)
+            m.density_bitfield.copy_(torch.from_numpy(lego_bitfield))
+        return m, NGPTrainer(m, lr=1e-2)
+
+    n, seed = 1024, 1234
+    m1, t1 = build()
+    fs1 = StaticTrainStep(t1, n, samples_per_ray_capacity=64, use_graph=use_graph)
+    fs1.attach_ray_source(ds.rays, ds.poses, ds.directions, seed=seed)
+    m2, t2 = build()
+    fs2 = StaticTrainStep(t2, n, samples_per_ray_capacity=64, use_graph=use_graph)
+    bank, poses, dirs = (t.cpu().numpy() for t in (ds.rays, ds.poses, ds.directions))
+    for step in range(3):
+        l1 = float(fs1.step_sampled())
+        b = O.sample_ray_batch(bank, poses, dirs, n, seed=seed, step=step)
+        for k in ("rays_o", "rays_d", "noise"):
+            np.testing.assert_array_equal(getattr(fs1, k).cpu().numpy(), b[k], err_msg=k)
+        np.testing.assert_array_equal(fs1.gt.cpu().numpy(), b["rgb"])
+        l2 = float(fs2.step(*(torch.from_numpy(b[k]).cuda() for k in ("rays_o", "rays_d", "rgb", "noise"))))
+        assert abs(l1 - l2) < 2e-3 * max(l2, 1e-6), (step, l1, l2)
+    assert int(fs1.counter[0]) > 500
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert float(((p1 - p2).abs() > 2e-3).float().mean()) < 2e-3
+    if use_graph:
+        assert fs1.kernels_per_replay_sampled == fs1.kernels_per_replay + 1 and fs1.replays_sampled == 3

@@ -523,3 +523,32 @@ def test_ray_head_fused_equals_separate_kernels(ops, oracle, dense):
     assert abs(float(loss_sum) - float((diff.astype(np.float64) ** 2).sum())) < 1e-3 * float((diff ** 2).sum())
     assert np.abs(N(dsig) - dsig_ref).max() <= 2e-3 * np.abs(dsig_ref).max()
     assert np.abs(N(drgbs).astype(np.float32) - drgbs_ref.astype(np.float32)).max() <= 3e-3 * max(1.0, np.abs(drgbs_ref.astype(np.float32)).max())
+
+
+@pytest.mark.gpu
+def test_sample_ray_batch_bit_exact(ops, oracle):
+    """ngp_sample_ray_batch == oracle for both index sources (given indices / Philox by (seed, step, ray))."""
+    rng = np.random.default_rng(9)
+    n_img, n_pix, n = 13, 40 * 30, 10007
+    poses = rng.standard_normal((n_img, 3, 4)).astype(np.float32)
+    dirs = rng.standard_normal((n_pix, 3)).astype(np.float32)
+    bank = rng.random((n_img, n_pix, 3)).astype(np.float32)
+    tb, tp, td = (torch.from_numpy(a).cuda() for a in (bank, poses, dirs))
+    step_dev = torch.tensor([77], device="cuda", dtype=torch.int32)
+    for kw_gpu, kw_cpu in [
+        (dict(seed=2**40 + 5, step=9), dict(seed=2**40 + 5, step=9)),
+        (dict(seed=3, step_dev=step_dev), dict(seed=3, step=77)),
+        (dict(seed=3, fixed_img=4), dict(seed=3, fixed_img=4)),
+    ]:
+        got = ops.sample_ray_batch(tb, tp, td, n, return_indices=True, **kw_gpu)
+        want = oracle.sample_ray_batch(bank, poses, dirs, n, **kw_cpu)
+        for k in ("img_idxs", "pix_idxs", "rays_o", "rays_d", "rgb", "noise"):
+            np.testing.assert_array_equal(got[k].cpu().numpy(), want[k], err_msg=k)
+    ii = torch.from_numpy(rng.integers(0, n_img, n)).cuda()
+    pi = torch.from_numpy(rng.integers(0, n_pix, n)).cuda()
+    got = ops.sample_ray_batch(tb, tp, td, n, img_idxs=ii, pix_idxs=pi, with_noise=False)
+    want = oracle.sample_ray_batch(bank, poses, dirs, n, img_idxs=ii.cpu().numpy(), pix_idxs=pi.cpu().numpy())
+    for k in ("rays_o", "rays_d", "rgb"):
+        np.testing.assert_array_equal(got[k].cpu().numpy(), want[k], err_msg=k)
+    assert got["noise"] is None
+    assert ops.sample_ray_batch(tb, tp, td, 0)["rays_o"].shape == (0, 3)

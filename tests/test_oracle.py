@@ -461,3 +461,52 @@ def test_distortion_matches_numpy_and_fd(oracle):
         fd = ((oracle.distortion_fwd(wp, deltas, ts, rays_a).astype(np.float64) -
                oracle.distortion_fwd(wm, deltas, ts, rays_a)) * g).sum() / (2 * eps)
         assert abs(fd - dws[s]) < 2e-3 * max(1.0, abs(fd)), (s, fd, dws[s])
+
+
+def test_philox_known_answers(oracle):
+    """Random123 kat_vectors for philox4x32 with 10 rounds — pins the generator behind the ray sampler."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, want in kat:
+        got = oracle.philox4x32_10(np.array(ctr, np.uint32), np.array(key, np.uint32))
+        assert [int(x) for x in got] == want
+
+
+def test_sample_ray_batch_matches_dataset_and_get_rays(oracle):
+    """Given the reference's own img/pix indices, the sampler equals the gather + get_rays of
+    datasets/base.py:53-60 and datasets/ray_utils.py:67-75; its own draws are uniform and step-dependent."""
+    from datasets.ray_utils import get_ray_directions, get_rays
+    rng = np.random.default_rng(5)
+    H = W = 24
+    n_img, n = 7, 4096
+    K = torch.tensor([[30.0, 0, W / 2], [0, 30.0, H / 2], [0, 0, 1]])
+    dirs = get_ray_directions(H, W, K).numpy()
+    poses = rng.standard_normal((n_img, 3, 4)).astype(np.float32)
+    bank = rng.random((n_img, H * W, 4)).astype(np.float32)   # RGBA bank: only [:, :3] is sampled
+    ii = rng.integers(0, n_img, n)
+    pi = rng.integers(0, H * W, n)
+    got = oracle.sample_ray_batch(bank, poses, dirs, n, img_idxs=ii, pix_idxs=pi)
+    ro, rd = get_rays(torch.from_numpy(dirs[pi]), torch.from_numpy(poses[ii]))
+    np.testing.assert_array_equal(got["rays_o"], ro.numpy())
+    np.testing.assert_allclose(got["rays_d"], rd.numpy(), rtol=1e-6, atol=1e-6)   # torch's sum order is unspecified
+    np.testing.assert_array_equal(got["rgb"], bank[ii, pi, :3])
+    # own Philox draws: in range, roughly uniform, reproducible, different per step and per seed
+    a = oracle.sample_ray_batch(bank, poses, dirs, n, seed=11, step=3)
+    b = oracle.sample_ray_batch(bank, poses, dirs, n, seed=11, step=3)
+    c = oracle.sample_ray_batch(bank, poses, dirs, n, seed=11, step=4)
+    d = oracle.sample_ray_batch(bank, poses, dirs, n, seed=12, step=3)
+    assert a["img_idxs"].min() >= 0 and a["img_idxs"].max() == n_img - 1
+    assert a["pix_idxs"].min() >= 0 and a["pix_idxs"].max() < H * W
+    assert np.array_equal(a["pix_idxs"], b["pix_idxs"]) and np.array_equal(a["noise"], b["noise"])
+    assert (a["pix_idxs"] != c["pix_idxs"]).mean() > 0.9 and (a["pix_idxs"] != d["pix_idxs"]).mean() > 0.9
+    counts = np.bincount(a["img_idxs"], minlength=n_img)
+    assert counts.min() > n / n_img * 0.8
+    assert 0.0 <= a["noise"].min() and a["noise"].max() < 1.0 and abs(a["noise"].mean() - 0.5) < 0.02
+    np.testing.assert_array_equal(a["rgb"], bank[a["img_idxs"], a["pix_idxs"], :3])
+    # 'same_image' strategy (base.py:45-47)
+    e = oracle.sample_ray_batch(bank, poses, dirs, 64, fixed_img=2, seed=1)
+    assert (e["img_idxs"] == 2).all() and (e["rays_o"] == poses[2, :, 3]).all()
