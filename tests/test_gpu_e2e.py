@@ -268,3 +268,38 @@ def test_static_step_with_device_sampled_batches(lego_bitfield, use_graph):
         assert float(((p1 - p2).abs() > 2e-3).float().mean()) < 2e-3
     if use_graph:
         assert fs1.kernels_per_replay_sampled == fs1.kernels_per_replay + 1 and fs1.replays_sampled == 3
+
+
+def test_shipped_lego_model_renders_on_gpu():
+    """Known-answer test on the CUDA path: the reference's shipped, trained Lego deployment model (L=4 F=4 dense
+    grid, 16-wide MLPs; staged under oracle/_ref/ by __graft_entry__.build()) loaded with load_deployment_model and
+    rendered through render(test_time=True) must reproduce the oracle's golden image of the same rays
+    (tests/golden/lego_kat.png, made by oracle/kat_lego.py)."""
+    import os
+    import __graft_entry__ as g
+    from conftest import GOLDEN
+    if not g.stage_lego_fixture():
+        pytest.skip("shipped Lego weights not staged (needs one build() in the container that has /root/reference)")
+    from PIL import Image
+    from modules.networks import NGP
+    from modules.rendering import render
+    from modules.utils import load_deployment_model
+    model = NGP(scale=0.5, pos_encoder_type='hash', levels=4, feature_per_level=4, base_res=32, max_res=128,
+                log2_T=21, xyz_net_width=16, rgb_net_width=16, rgb_net_depth=1).cuda()
+    extra = load_deployment_model(model, g.LEGO_FIXTURE)
+    pose = torch.from_numpy(extra['pose'].reshape(3, 4).copy()).cuda()
+    directions = torch.from_numpy(extra['model.directions'].reshape(600, 300, 3)[::2, ::2].copy()).cuda()
+    h, w = directions.shape[:2]
+    dirs = directions.reshape(-1, 3)
+    rays_d = dirs @ pose[:, :3].T
+    rays_o = pose[:, 3].expand_as(rays_d).contiguous()
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
+        out = render(model, rays_o, rays_d, test_time=True, T_threshold=1e-2, exp_step_factor=0.0)
+    rgb = out['rgb'].float().reshape(h, w, 3).clamp(0, 1).cpu().numpy()   # render() composites onto white
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, 'lego_kat.png')).convert('RGB'), dtype=np.float32) / 255
+    assert gold.shape == rgb.shape
+    mse = float(((rgb - gold) ** 2).mean())
+    psnr = -10 * np.log10(max(mse, 1e-12))
+    assert psnr > 35.0, psnr          # fp16 autocast MLP + 8-bit golden; a layout mistake gives < 15 dB
+    opacity = out['opacity'].float().reshape(h, w).cpu().numpy()
+    assert 0.55 < float((opacity > 0.5).mean()) < 0.67   # tests/golden/lego_kat_stats.json: coverage 0.611
