@@ -59,6 +59,18 @@ constexpr int kSmemBytesBwd = kBarBwd + 32;  // 110,624 B -> 2 CTAs / SM
 constexpr uint32_t kTmemColsBwd = 256;
 constexpr uint32_t kColDW4 = 64, kColDW1 = 128, kColDW3 = 160, kColDW2T = 192, kColDW5T = 208;
 
+// ---- optional per-round clock trace (scripts/mlp_round_trace.py builds a separate library with -DNGP_MLP_TRACE)
+#ifdef NGP_MLP_TRACE
+__device__ long long g_mlp_trace[2 * 4 * 32];
+#define NGP_TR(k)                                                                                   \
+    do {                                                                                            \
+        if (blockIdx.x == 0 && (tid == 0 || tid == 160) && tile_no < 4)                             \
+            g_mlp_trace[(tid ? 128 : 0) + tile_no * 32 + (k)] = clock64();                          \
+    } while (0)
+#else
+#define NGP_TR(k) ((void)0)
+#endif
+
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -290,7 +302,10 @@ __global__ void __launch_bounds__(kThreads, 4) mlp_fwd_kernel(const TEmb* __rest
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     RowIn cur = load_row<TEmb, false>(emb, dirs, nullptr, nullptr, (int64_t)blockIdx.x * kTile + row,
                                       (int64_t)blockIdx.x * kTile + row < n, hh);
+    [[maybe_unused]] int tile_no = -1;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        ++tile_no;
+        NGP_TR(31);
         const int64_t i = tile * kTile + row;
         const bool valid = i < n;
 
@@ -307,26 +322,35 @@ __global__ void __launch_bounds__(kThreads, 4) mlp_fwd_kernel(const TEmb* __rest
         __syncthreads();
 
         // ---- layer 1: H1 = relu(X W1^T)                       [128x32]x[32x64]
+        NGP_TR(0);
         if (tid == 0) {
             tc_fence_after();
             issue_layer(tmem_base, aA, aW1, 32, 64, bar);
         }
+        NGP_TR(1);
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
+        NGP_TR(2);
         epilogue_hidden(tmem_row, smem + kBufB, row, hh);
+        NGP_TR(3);
         fence_proxy_async();
         tc_fence_before();
+        NGP_TR(4);
         __syncthreads();
+        NGP_TR(5);
 
         // ---- layer 2: h = H1 W2^T                             [128x64]x[64x16]
+        NGP_TR(6);
         if (tid == 0) {
             tc_fence_after();
             issue_layer(tmem_base, aB, aW2, 64, 16, bar);
         }
+        NGP_TR(7);
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
+        NGP_TR(8);
         if (hh == 0) {
             // sigma = TruncExp(h[:,0]) (networks.py:22-24, :146) and the geometry half of X3 = [SH | h]
             float h[16];
@@ -349,44 +373,62 @@ __global__ void __launch_bounds__(kThreads, 4) mlp_fwd_kernel(const TEmb* __rest
             *reinterpret_cast<uint4*>(dst + chunk_off(row, 1, 32)) =
                 make_uint4(pack_h2(e[8], e[9]), pack_h2(e[10], e[11]), pack_h2(e[12], e[13]), pack_h2(e[14], e[15]));
         }
+        NGP_TR(9);
         fence_proxy_async();
         tc_fence_before();
+        NGP_TR(10);
         __syncthreads();
+        NGP_TR(11);
 
         // ---- layer 3: H3 = relu(X3 W3^T)                      [128x32]x[32x64]
+        NGP_TR(12);
         if (tid == 0) {
             tc_fence_after();
             issue_layer(tmem_base, aA, aW3, 32, 64, bar);
         }
+        NGP_TR(13);
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
+        NGP_TR(14);
         epilogue_hidden(tmem_row, smem + kBufB, row, hh);
+        NGP_TR(15);
         fence_proxy_async();
         tc_fence_before();
+        NGP_TR(16);
         __syncthreads();
+        NGP_TR(17);
 
         // ---- layer 4: H4 = relu(H3 W4^T)                      [128x64]x[64x64]
+        NGP_TR(18);
         if (tid == 0) {
             tc_fence_after();
             issue_layer(tmem_base, aB, aW4, 64, 64, bar);
         }
+        NGP_TR(19);
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
+        NGP_TR(20);
         epilogue_hidden(tmem_row, smem + kBufA, row, hh);
+        NGP_TR(21);
         fence_proxy_async();
         tc_fence_before();
+        NGP_TR(22);
         __syncthreads();
+        NGP_TR(23);
 
         // ---- layer 5: rgb = sigmoid(H4 W5^T)                  [128x64]x[64x16(3 used)]
+        NGP_TR(24);
         if (tid == 0) {
             tc_fence_after();
             issue_layer(tmem_base, aA, aW5, 64, 16, bar);
         }
+        NGP_TR(25);
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
+        NGP_TR(26);
         if (hh == 0) {
             float o[16];
             tmem_ld16(tmem_row, o);
@@ -398,6 +440,7 @@ __global__ void __launch_bounds__(kThreads, 4) mlp_fwd_kernel(const TEmb* __rest
                 }
             }
         }
+        NGP_TR(27);
         tc_fence_before();
         __syncthreads();  // bufA / TMEM are reused by the next tile
     }
@@ -735,6 +778,12 @@ int launch_fwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, flo
 }
 
 }  // namespace
+
+#ifdef NGP_MLP_TRACE
+extern "C" int ngp_debug_mlp_trace(long long* out_host) {
+    return (int)cudaMemcpyFromSymbol(out_host, g_mlp_trace, sizeof(long long) * 256);
+}
+#endif
 
 extern "C" {
 
