@@ -37,6 +37,9 @@ _FLAGS = [
     ('--gpu', dict(type=int, default=0, help='set cuda device (ignored under torchrun: LOCAL_RANK wins)')),
     ('--ckpt_path', dict(type=str, default=None, help='pretrained checkpoint to load')),
     ('--gui', dict(action='store_true', default=False, help='render an orbit with the GUI camera after training')),
+    ('--graph_step', dict(action='store_true', default=False,
+                          help='run the training step as one CUDA-graph replay (StaticTrainStep; stock NGP '
+                               'architecture, no distortion loss); same update as the default module path')),
     ('--deployment', dict(action='store_true', default=False)),
     ('--deployment_model_path', dict(type=str, default='./')),
 ]

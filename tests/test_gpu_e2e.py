@@ -43,12 +43,15 @@ def test_fused_mlp_path_equals_torch_path():
     assert (c_f.float() - c_t.float()).abs().max() <= 3e-3
 
 
-def test_training_on_analytic_scene_reaches_psnr(tmp_path, monkeypatch):
-    """train.py end to end (small config): PSNR against the analytic teacher's held-out views."""
+@pytest.mark.parametrize("extra", [[], ['--graph_step']])
+def test_training_on_analytic_scene_reaches_psnr(tmp_path, monkeypatch, extra):
+    """train.py end to end (small config): PSNR against the analytic teacher's held-out views, through the module /
+    autograd step and through the graph-captured step."""
     import train
     monkeypatch.chdir(tmp_path)
     monkeypatch.setattr(train, 'dataset_dict', {'synthetic': _small_dataset})
-    psnrs = train.main(['--dataset_name', 'synthetic', '--half_opt', '--batch_size', '4096', '--max_steps', '400'])
+    psnrs = train.main(['--dataset_name', 'synthetic', '--half_opt', '--batch_size', '4096', '--max_steps', '400']
+                       + extra)
     assert (tmp_path / 'results' / 'model.pth').exists() and (tmp_path / 'results' / 'rgb_000.png').exists()
     assert min(psnrs) > 22.0, psnrs
 

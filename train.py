@@ -81,6 +81,13 @@ def main(prefix_args=None):
     torch.manual_seed(seed + rank)  # data / marching noise differ per rank from here on
     trainer = NGPTrainer(model, lr=hparams.lr, max_steps=hparams.max_steps)
 
+    fast = None
+    if hparams.graph_step:
+        if hparams.distortion_loss_w > 0 or not model._fusable(next(model.parameters())):
+            raise ValueError("--graph_step needs the stock NGP architecture and --distortion_loss_w 0")
+        from taichi_nerfs_b200.fast_step import StaticTrainStep
+        fast = StaticTrainStep(trainer, hparams.batch_size, exp_step_factor=exp_step_factor)
+
     tic = time.time()
     for step in range(hparams.max_steps + 1):
         model.train()
@@ -92,7 +99,11 @@ def main(prefix_args=None):
         extra_loss = None
         if hparams.distortion_loss_w > 0:
             extra_loss = lambda res: hparams.distortion_loss_w * distortion_loss(res).mean()  # noqa: E731
-        loss, results = trainer.step(rays_o, rays_d, data['rgb'], exp_step_factor, extra_loss=extra_loss)
+        if fast is not None:   # one graph replay, nothing synchronises the host
+            loss = fast.step(rays_o, rays_d, data['rgb'])
+            results = {'rgb': fast.rgb, 'rm_samples': fast.counter[0], 'vr_samples': fast.counter[0]}
+        else:
+            loss, results = trainer.step(rays_o, rays_d, data['rgb'], exp_step_factor, extra_loss=extra_loss)
 
         if step % 1000 == 0 and rank == 0:
             with torch.no_grad():
