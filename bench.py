@@ -165,7 +165,8 @@ def run_ours(args):
 
     sample_counts = []
     from taichi_nerfs_b200.fast_step import StaticTrainStep
-    fast = None if args.path == "modules" else StaticTrainStep(trainer, BATCH, samples_per_ray_capacity=384)
+    fast = None if args.path == "modules" else StaticTrainStep(trainer, BATCH, samples_per_ray_capacity=384,
+                                                               overlap_optimizer=not args.no_overlap)
     if fast is not None:
         # the training set stays resident in HBM (train.py: `train_dataset.to(device)`), and the step draws its own
         # batch on the device (datasets/base.py:34-61 + get_rays as the first node of the graph)
@@ -175,6 +176,8 @@ def run_ours(args):
     def one_step(step_idx, b):
         with torch.autocast("cuda", dtype=torch.float16):
             if step_idx % UPDATE_INTERVAL == 0:
+                if fast is not None:
+                    fast.flush()   # overlap mode: the grid update must see the parameters of the last step
                 model.update_density_grid(DENSITY_THRESHOLD, warmup=step_idx < 256)
         if fast is not None and b is None:   # batch sampling + the whole step = one CUDA-graph replay, no host sync
             loss = fast.step_sampled()
@@ -230,14 +233,17 @@ def run_ours(args):
     for s in range(args.warmup):
         one_step(s, batches[s])
     launches0 = _lib.launch_count()
-    replays0 = fast.replays if fast is not None else 0
-    sampled0 = fast.replays_sampled if fast is not None else 0
-    ms_total = timed(lambda: [one_step(args.warmup + k, batches[args.warmup + k]) for k in range(args.steps)])
+    def timed_steps():
+        for k in range(args.steps):
+            one_step(args.warmup + k, batches[args.warmup + k])
+        if fast is not None:
+            fast.flush()   # every one of the K updates is applied inside the timed region
+    graph0 = fast.graph_kernel_launches if fast is not None else 0
+    ms_total = timed(timed_steps)
     clock_info = clocks.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0   # eager launches of libngp_b200 kernels
     if fast is not None:                          # + kernel nodes executed by CUDA-graph replays
-        launches += (fast.replays - replays0) * fast.kernels_per_replay
-        launches += (fast.replays_sampled - sampled0) * fast.kernels_per_replay_sampled
+        launches += fast.graph_kernel_launches - graph0
     ms_step = ms_total / args.steps
     value = world * BATCH / (ms_step * 1e-3)
     spr = float(torch.stack([c.float() for c in sample_counts[-args.steps:]]).mean()) / BATCH
@@ -251,7 +257,12 @@ def run_ours(args):
     base = args.warmup + args.steps
     for s in range(min(3, args.warmup)):
         e2e_step(base + s, host_batches[s])
-    ms_e2e = timed(lambda: [e2e_step(base + 3 + k, host_batches[args.warmup + k]) for k in range(args.steps)])
+    def timed_e2e():
+        for k in range(args.steps):
+            e2e_step(base + 3 + k, host_batches[args.warmup + k])
+        if fast is not None:
+            fast.flush()
+    ms_e2e = timed(timed_e2e)
     e2e_value = world * BATCH / (ms_e2e / args.steps * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
@@ -283,6 +294,9 @@ def run_ours(args):
                    "step_path": "StaticTrainStep: batch sampling (resident 100x800x800 training set) + whole step = one "
                                 "CUDA-graph replay, sample count stays on the device; e2e arm: host batches -> get_rays -> "
                                 "the same graph without the sampler node"
+                                + ("" if args.no_overlap else "; optimizer of step k runs on a parallel graph branch "
+                                   "beside ray_aabb + marching of step k+1 (flushed before every grid update and at "
+                                   "the end of the timed region)")
                                 if fast is not None else "modules API: render() + torch.autograd + fused Adam"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
@@ -450,6 +464,9 @@ def main():
     ap.add_argument("--path", default="graph", choices=["graph", "modules"],
                     help="graph: StaticTrainStep (one CUDA graph per step, sync-free); "
                          "modules: render()+autograd through the reference-shaped module API")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="graph path: run the optimizer at the end of its own step instead of next to the next "
+                         "step's marching")
     ap.add_argument("--ncu-window", type=int, default=0,
                     help="profiling aid: wrap this many extra steps in cudaProfilerStart/Stop "
                          "(use with `ncu --profile-from-start off`); numbers printed under ncu are not bench values")

@@ -176,6 +176,12 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// relu fused into the conversion (one F2FP instead of two FMNMX + F2FP); low half = a
+__device__ __forceinline__ uint32_t pack_h2_relu(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
 
 // copy a row-major fp32 weight [rows x K] into the interleaved fp16 operand layout (rows_pad rows)
 __device__ __forceinline__ void stage_weight(uint8_t* smem, const float* __restrict__ w, int rows, int rows_pad, int K) {
@@ -221,8 +227,8 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, uint8_t* dst,
     for (int kc = 0; kc < 4; ++kc) {
         const float* q = v + kc * 8;
         *reinterpret_cast<uint4*>(dst + chunk_off(row, hh * 4 + kc, 64)) =
-            make_uint4(pack_h2(fmaxf(q[0], 0.f), fmaxf(q[1], 0.f)), pack_h2(fmaxf(q[2], 0.f), fmaxf(q[3], 0.f)),
-                       pack_h2(fmaxf(q[4], 0.f), fmaxf(q[5], 0.f)), pack_h2(fmaxf(q[6], 0.f), fmaxf(q[7], 0.f)));
+            make_uint4(pack_h2_relu(q[0], q[1]), pack_h2_relu(q[2], q[3]), pack_h2_relu(q[4], q[5]),
+                       pack_h2_relu(q[6], q[7]));
     }
 }
 

@@ -31,7 +31,7 @@ def _p(t):
 class StaticTrainStep:
     def __init__(self, trainer, n_rays: int, samples_per_ray_capacity: int = 384, exp_step_factor: float = 0.0,
                  T_threshold: float = 1e-4, max_samples: int = 1024, use_graph: bool = True,
-                 dynamic_loss_scale: bool = True):
+                 dynamic_loss_scale: bool = True, overlap_optimizer: bool = False):
         self.tr = trainer
         m = self.model = trainer.model
         enc = m.pos_encoder
@@ -61,6 +61,7 @@ class StaticTrainStep:
         self.loss_sum = z(1)
         # optimizer scalars on the device
         self.step_dev = torch.full((1,), trainer.step_count, device=dev, dtype=i32)
+        self.sample_step = torch.full((1,), trainer.step_count, device=dev, dtype=i32)   # batches drawn so far
         self.hyper = z(3)
         # GradScaler state on the device: [scale, growth_tracker (int bits)]; growth 2x / 2000 clean steps, backoff 0.5
         self.dynamic_loss_scale = bool(dynamic_loss_scale)
@@ -79,25 +80,51 @@ class StaticTrainStep:
         self.rays_o[:] = torch.tensor([1.2, 0.3, 0.5], device=dev)
         jitter = (torch.arange(self.n, device=dev, dtype=f32)[:, None] % 97) * 1e-3
         self.rays_d[:] = -self.rays_o + jitter * torch.tensor([0.3, -0.2, 0.1], device=dev)
-        self.graph = None
-        self.graph_sampled = None      # second graph with the ray-batch sampler as its first node
+        # graphs by (sampled, mode): mode "sync" = forward/backward + optimizer; with overlap_optimizer the optimizer
+        # of step k runs at the head of step k+1's graph on a parallel branch next to ray_aabb + marching (which only
+        # read the occupancy bitfield): "first" = forward/backward only, "steady" = optimizer(k-1) || march(k), then
+        # the network part of step k.  flush() applies the pending update.
+        self._graphs, self._kernels = {}, {}
         self.src = None
-        self.kernels_per_replay = 0
-        self.kernels_per_replay_sampled = 0
         self.replays = 0
         self.replays_sampled = 0
+        self.graph_kernel_launches = 0   # libngp_b200 kernel nodes executed by graph replays so far
+        self.overlap = bool(overlap_optimizer)
+        self.pending = False             # gradients of the last step not applied yet (overlap mode only)
+        self._side = torch.cuda.Stream(device=dev, priority=-1)
         self.use_graph = bool(use_graph)
         if self.use_graph:
             try:
                 # with world_size > 1 the NCCL all-reduce is captured as a graph node too
-                self.graph, self.kernels_per_replay = self._capture(sampled=False)
+                for mode in self._modes():
+                    self._capture(False, mode)
             except RuntimeError as e:  # pragma: no cover - depends on the NCCL / driver combination
                 if parallel.world_info(trainer.pg)[1] == 1:
                     raise
                 print(f"[StaticTrainStep] CUDA-graph capture with NCCL failed ({e}); falling back to eager enqueue")
-                self.graph = None
+                self._graphs, self._kernels = {}, {}
                 self.use_graph = False
                 torch.cuda.synchronize()
+
+    def _modes(self):
+        return ("first", "steady") if self.overlap else ("sync",)
+
+    # sync-mode views kept for callers that count launches
+    @property
+    def graph(self):
+        return self._graphs.get((False, self._modes()[-1]))
+
+    @property
+    def graph_sampled(self):
+        return self._graphs.get((True, self._modes()[-1]))
+
+    @property
+    def kernels_per_replay(self):
+        return self._kernels.get((False, self._modes()[-1]), 0)
+
+    @property
+    def kernels_per_replay_sampled(self):
+        return self._kernels.get((True, self._modes()[-1]), 0)
 
     # ---------------------------------------------------------------------------------------------
     def _st(self):
@@ -106,9 +133,8 @@ class StaticTrainStep:
     def _table(self):
         return self.tr._shadow if self.half else self.model.pos_encoder.hash_table.data
 
-    def _enqueue_forward_backward(self):
+    def _enqueue_march(self):
         L, m, st, n, cap = load(), self.model, self._st(), self.n, self.cap
-        tag = F16 if self.half else F32
         bits = m.density_bitfield
         check(L.ngp_ray_aabb_intersect(_p(self.rays_o), _p(self.rays_d), float(m.scale), _p(self.hits), n, st))
         # single-pass march: every ray reserves its rows with one atomic (row order across rays is arbitrary, as
@@ -118,6 +144,10 @@ class StaticTrainStep:
                                       m.cascades, m.grid_size, float(m.scale), self.esf, self.max_samples,
                                       _p(self.counter), _p(self.rays_a), _p(self.xyzs), _p(self.dirs),
                                       _p(self.deltas), _p(self.ts), n, cap, st))
+
+    def _enqueue_network(self):
+        L, m, st, n, cap = load(), self.model, self._st(), self.n, self.cap
+        tag = F16 if self.half else F32
         nd = _p(self.counter)  # counter[0] = number of valid sample rows, read on the device
         check(L.ngp_hash_encode_fwd_dyn(_p(self.xyzs), _p(self._table()), C.byref(self._clayout), _p(self.emb), tag,
                                         cap, nd, self.aabb6, st))
@@ -157,38 +187,56 @@ class StaticTrainStep:
                                           _p(self.hyper), st))
 
     def _enqueue_sampler(self):
-        """datasets/base.py:34-61 + ray_utils.py:51-80 + the marching jitter, keyed by (seed, step_dev, ray)."""
+        """datasets/base.py:34-61 + ray_utils.py:51-80 + the marching jitter, keyed by (seed, batch counter, ray)."""
         src = self.src
         check(load().ngp_sample_ray_batch(_p(src["bank"]), src["bank"].shape[2], _p(src["poses"]), _p(src["dirs"]),
                                           src["poses"].shape[0], src["dirs"].shape[0], None, None, src["fixed_img"],
-                                          src["seed"], _p(self.step_dev), 0, _p(self.rays_o), _p(self.rays_d),
+                                          src["seed"], _p(self.sample_step), 0, _p(self.rays_o), _p(self.rays_d),
                                           _p(self.gt), _p(self.noise), None, None, self.n, self._st()))
+        self.sample_step.add_(1)   # own batch counter: step_dev moves with the optimizer, which may run a step late
 
-    def _enqueue(self, sampled=False):
-        if sampled:
-            self._enqueue_sampler()
-        self._enqueue_forward_backward()
+    def _enqueue_update(self):
         if self.tr.world_size > 1:
             parallel.allreduce_gradients(self.tr.flat_grad, self.tr.pg)
         self._enqueue_optimizer()
 
-    def _capture(self, sampled):
+    def _enqueue(self, sampled=False, mode="sync"):
+        if sampled:
+            self._enqueue_sampler()
+        if mode == "steady":
+            # optimizer of the PREVIOUS step beside this step's ray_aabb + marching.  The marching branch runs on
+            # a high-priority stream (the priority is kept by the captured kernel nodes): its latency-bound warps
+            # take SM slots first and the bandwidth-bound Adam sweep fills in around them.
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._enqueue_march()
+            self._enqueue_update()
+            main.wait_stream(self._side)
+            self._enqueue_network()
+            return
+        self._enqueue_march()
+        self._enqueue_network()
+        if mode == "sync":
+            self._enqueue_update()
+
+    def _capture(self, sampled, mode):
         # the graph must not mutate training state while being built: snapshot, warm up + capture, restore
         tr = self.tr
         keep = [p.data.clone() for p in tr.params] + [tr.exp_avg.clone(), tr.exp_avg_sq.clone(), self.step_dev.clone()]
-        scale_keep, hyper_keep = self.scale_state.clone(), self.hyper.clone()
+        scale_keep, hyper_keep, sample_keep = self.scale_state.clone(), self.hyper.clone(), self.sample_step.clone()
         shadow = None if tr._shadow is None else tr._shadow.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                self._enqueue(sampled)
+                self._enqueue(sampled, mode)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
         with torch.cuda.graph(graph):
-            self._enqueue(sampled)
+            self._enqueue(sampled, mode)
         kernels = _lib.launch_count() - before  # libngp_b200 kernel nodes in the graph
         torch.cuda.synchronize()
         for p, k in zip(tr.params, keep):
@@ -198,10 +246,11 @@ class StaticTrainStep:
         self.step_dev.copy_(keep[-1])
         self.scale_state.copy_(scale_keep)
         self.hyper.copy_(hyper_keep)
+        self.sample_step.copy_(sample_keep)
         tr.flat_grad.zero_()
         if shadow is not None:
             tr._shadow.copy_(shadow)
-        return graph, kernels
+        self._graphs[(sampled, mode)], self._kernels[(sampled, mode)] = graph, kernels
 
     # ---------------------------------------------------------------------------------------------
     def step(self, rays_o, rays_d, rgb_gt, noise=None):
@@ -213,12 +262,27 @@ class StaticTrainStep:
             self.noise.uniform_()
         else:
             self.noise.copy_(noise, non_blocking=True)
-        if self.graph is not None:
-            self.graph.replay()
-            self.replays += 1
-        else:
-            self._enqueue()
+        self._run(False)
+        self.replays += 1 if self.use_graph else 0
         return self._finish_step()
+
+    def _run(self, sampled):
+        mode = "sync" if not self.overlap else ("steady" if self.pending else "first")
+        if self.use_graph:
+            self._graphs[(sampled, mode)].replay()
+            self.graph_kernel_launches += self._kernels[(sampled, mode)]
+        else:
+            self._enqueue(sampled, mode)
+        self.pending = self.overlap
+
+    def flush(self):
+        """Overlap mode: apply the optimizer update of the last step now (before anything reads the parameters:
+        update_density_grid, rendering, checkpoints).  No-op otherwise."""
+        if self.pending:
+            self._enqueue_update()
+            self.pending = False
+            if self.tr._shadow is not None:
+                self.model.pos_encoder.adopt_shadow(self.tr._shadow)
 
     def _finish_step(self):
         self.tr.step_count += 1
@@ -238,18 +302,17 @@ class StaticTrainStep:
         self.src = dict(bank=bank, poses=poses.reshape(-1, 3, 4), dirs=directions, seed=int(seed),
                         fixed_img=int(fixed_img))
         if self.use_graph:
-            self.graph_sampled, self.kernels_per_replay_sampled = self._capture(sampled=True)
+            self.flush()
+            for mode in self._modes():
+                self._capture(True, mode)
         return self
 
     def step_sampled(self):
         """One training step on a batch drawn on the device (no host input, no host sync)."""
         if self.src is None:
             raise _lib.NgpError("step_sampled() needs attach_ray_source() first")
-        if self.graph_sampled is not None:
-            self.graph_sampled.replay()
-            self.replays_sampled += 1
-        else:
-            self._enqueue(sampled=True)
+        self._run(True)
+        self.replays_sampled += 1 if self.use_graph else 0
         return self._finish_step()
 
     def stats(self):

@@ -271,6 +271,7 @@ def test_static_step_with_device_sampled_batches(lego_bitfield, use_graph):
         assert float(((p1 - p2).abs() > 2e-3).float().mean()) < 2e-3
     if use_graph:
         assert fs1.kernels_per_replay_sampled == fs1.kernels_per_replay + 1 and fs1.replays_sampled == 3
+        assert int(fs1.sample_step) == 3
 
 
 def test_shipped_lego_model_renders_on_gpu():
@@ -306,3 +307,49 @@ def test_shipped_lego_model_renders_on_gpu():
     assert psnr > 35.0, psnr          # fp16 autocast MLP + 8-bit golden; a layout mistake gives < 15 dB
     opacity = out['opacity'].float().reshape(h, w).cpu().numpy()
     assert 0.55 < float((opacity > 0.5).mean()) < 0.67   # tests/golden/lego_kat_stats.json: coverage 0.611
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_static_step_optimizer_overlap_equals_sync_step(lego_bitfield, use_graph):
+    """overlap_optimizer=True (Adam of step k on a graph branch beside the marching of step k+1, flush() at the
+    end) applies exactly the same sequence of updates as the default step."""
+    from modules.networks import NGP
+    from oracle.train_step import make_rays
+    from taichi_nerfs_b200.fast_step import StaticTrainStep
+    from taichi_nerfs_b200.trainer import NGPTrainer
+
+    def build():
+        torch.manual_seed(3)
+        m = NGP(scale=0.5, max_res=1024, half_opt=True).cuda()
+        with torch.no_grad():
+            m.pos_encoder.hash_table.mul_(2e3)
+            m.density_bitfield.copy_(torch.from_numpy(lego_bitfield))
+        return m, NGPTrainer(m, lr=1e-2)
+
+    n = 2048
+    batches = []
+    for k in range(4):
+        o, d = make_rays(n, seed=20 + k)
+        g = torch.Generator(device='cuda').manual_seed(k)
+        batches.append((torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(),
+                        torch.rand(n, 3, device='cuda', generator=g), torch.rand(n, device='cuda', generator=g)))
+    m1, t1 = build()
+    fs1 = StaticTrainStep(t1, n, samples_per_ray_capacity=64, use_graph=use_graph)
+    l1 = [float(fs1.step(*b)) for b in batches]
+    m2, t2 = build()
+    fs2 = StaticTrainStep(t2, n, samples_per_ray_capacity=64, use_graph=use_graph, overlap_optimizer=True)
+    l2 = []
+    for k, b in enumerate(batches):
+        l2.append(float(fs2.step(*b)))
+        assert fs2.pending and int(fs2.step_dev) == k      # the update of step k is still outstanding
+        if k == 1:
+            fs2.flush()                                      # e.g. before a density-grid update
+            assert not fs2.pending and int(fs2.step_dev) == 2
+    fs2.flush()
+    fs2.flush()                                              # idempotent
+    assert int(fs2.step_dev) == 4 == int(fs1.step_dev)
+    for a, b in zip(l1, l2):
+        assert abs(a - b) < 2e-3 * max(a, 1e-6), (l1, l2)
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        assert float(((p1 - p2).abs() > 2e-3).float().mean()) < 2e-3
+    assert float(t2.flat_grad.abs().max()) == 0.0           # Adam zeroed the gradient buffer
