@@ -38,7 +38,7 @@ BYTES_PER_SAMPLE = {"hash_fwd": 588, "hash_bwd": 1100, "mlp_fwd": 86, "mlp_bwd":
 
 
 # DRAM bytes per launch of each kernel from the committed `ncu --set full` capture (profiles/), same workload
-NCU_DRAM_BYTES_PER_LAUNCH = {"hash_bwd": 215.37e6 + 3.66e6, "hash_fwd": 49.69e6 + 99.32e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {"hash_bwd": 215.3e6, "hash_fwd": 146.0e6, "mlp_bwd": 288.2e6, "mlp_fwd": 181.2e6}
 
 
 def measured_peaks():
@@ -220,6 +220,9 @@ def run_ours(args):
             one_step(1 + s, batches[s % len(batches)])
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        if rank == 0:
+            print(json.dumps({"ncu_window_steps": args.ncu_window,
+                              "samples_per_step": [int(c) for c in sample_counts[-args.ncu_window:]]}))
         return
 
     # ---- device-resident arm ("value") -------------------------------------------------------------
@@ -364,7 +367,7 @@ def kernel_roofline(torch, ops, model, trainer, ds, get_rays, dev):
     return {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(top), "traffic_unit": "bytes/launch",
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, "
-                              "profiles/r1_ncu_summary_after_hash_march_opt.txt (S=2.19 M samples)",
+                              "profiles/r1_kernels_ncu_table_final.md (one graph step, S=2.19 M samples)",
             "peak_source": peak_src, "samples": S,
             "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE[top], "kernel_ms": times,
             "note": "fp16 table (21.8 MiB) + fp32 grad (43.6 MiB) fit the 126 MB L2: gathers/atomics are L2-bound, "
@@ -401,7 +404,7 @@ def oracle_workload(n_rays, seed):
     return TS, model, batch
 
 
-def cpu_baseline(budget_s=20.0, n_rays=256):
+def cpu_baseline(budget_s=20.0, n_rays=2048):
     TS, model, batch = oracle_workload(n_rays, SEED)
     cores = len(os.sched_getaffinity(0))
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
@@ -425,9 +428,22 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_rays = args.ref_rays
-    TS, model, batch = oracle_workload(n_rays, SEED)
     cores = len(os.sched_getaffinity(0))
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    n_rays = args.ref_rays
+    if n_rays <= 0:
+        # as much of the 8192-ray batch per step as fits a ~2 minute run on this host (per-step fixed costs -
+        # Adam over 11.4 M parameters, gradient zeroing - are amortised as in the real workload)
+        TS, model, batch = oracle_workload(256, SEED)
+        o, d, gt, nz = batch(0)
+        TS.train_step(model, o, d, gt, nz)
+        t0 = time.perf_counter()
+        TS.train_step(model, *batch(1))
+        per_ray = (time.perf_counter() - t0) / 256
+        n_rays = 256
+        while n_rays < BATCH and (args.steps + args.warmup) * (2 * n_rays) * per_ray <= 120.0:
+            n_rays *= 2
+    TS, model, batch = oracle_workload(n_rays, SEED)
     for s in range(args.warmup):
         o, d, gt, nz = batch(s)
         TS.train_step(model, o, d, gt, nz)
@@ -460,7 +476,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
-    ap.add_argument("--ref-rays", type=int, default=256, help="rays per step of the reference arm's bounded sample")
+    ap.add_argument("--ref-rays", type=int, default=0,
+                    help="rays per step of the reference arm's bounded sample (0 = as many of the 8192 as fit ~2 min)")
     ap.add_argument("--path", default="graph", choices=["graph", "modules"],
                     help="graph: StaticTrainStep (one CUDA graph per step, sync-free); "
                          "modules: render()+autograd through the reference-shaped module API")

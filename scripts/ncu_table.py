@@ -10,6 +10,8 @@ ALG = {  # algorithmic bytes per sample (SURVEY.md §8d, fp16 encoder) / per ray
     "hash_fwd": ("sample", 588), "hash_bwd": ("sample", 1100), "mlp_fwd": ("sample", 86), "mlp_bwd": ("sample", 150),
     "composite_train_fwd": ("sample", 22), "composite_train_bwd": ("sample", 32), "march_train_warp_kernel<1>": ("sample", 32),
     "march_train_warp_kernel<0>": ("ray", 48), "adam_kernel": ("param", 34),
+    "march_train_warp_kernel<2>": ("sample", 32), "ray_head_fused_kernel": ("sample", 24),
+    "sample_ray_batch_kernel": ("ray", 72), "check_finite_kernel": ("param", 4),
 }
 rows = list(csv.reader(open(sys.argv[1])))
 S = float(sys.argv[2])
