@@ -177,6 +177,10 @@ int ngp_adam_hyper_update(int32_t* step_dev, float lr0, float lr_min, int32_t ma
  * scale *= growth.  Also refreshes hyper_dev[2] = 1 / (scale * world_size) for the NEXT step's Adam. */
 int ngp_loss_scale_update(float* state_dev, const int32_t* found_inf, float growth, float backoff,
                           int32_t growth_interval, float world_size, float* hyper_dev, void* stream);
+/* the scalar housekeeping the reference does with tensor ops every step, in one launch (each pointer may be
+ * NULL): counter[0:2] = 0 (modules/ray_march.py:183 `counter.zero_()`), *loss_sum = 0, *found_inf = 0
+ * (GradScaler's per-step found_inf tensor), *batch_counter += 1 (batches drawn by ngp_sample_ray_batch) */
+int ngp_step_reset(int32_t* march_counter2, float* loss_sum, int32_t* found_inf, int32_t* batch_counter, void* stream);
 /* per-ray loss head: out = rgb + bg*(1-opacity) (modules/rendering.py:219-226), loss = mean((out-gt)^2)
  * (train.py:193), and d(loss*loss_scale)/d rgb, /d opacity in one launch.  *loss_sum accumulates
  * sum((out-gt)^2) (caller zeroes it; divide by 3*n_rays). */

@@ -89,6 +89,16 @@ __global__ void adam_hyper_kernel(int32_t* __restrict__ step_dev, float lr0, flo
     *step_dev = s + 1;
 }
 
+// per-step scalar housekeeping in one launch (each pointer optional)
+__global__ void step_reset_kernel(int32_t* __restrict__ counter2, float* __restrict__ loss_sum,
+                                  int32_t* __restrict__ found_inf, int32_t* __restrict__ batch_counter) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (counter2) counter2[0] = counter2[1] = 0;
+    if (loss_sum) *loss_sum = 0.0f;
+    if (found_inf) *found_inf = 0;
+    if (batch_counter) *batch_counter += 1;
+}
+
 // GradScaler.update(): torch/amp/grad_scaler.py -> _amp_update_scale_
 __global__ void loss_scale_update_kernel(float* __restrict__ state, const int32_t* __restrict__ found_inf, float growth,
                                          float backoff, int32_t interval, float world, float* __restrict__ hyper) {
@@ -203,6 +213,12 @@ int ngp_loss_scale_update(float* state_dev, const int32_t* found_inf, float grow
     loss_scale_update_kernel<<<1, 32, 0, ngp::as_stream(stream)>>>(state_dev, found_inf, growth, backoff, growth_interval,
                                                                    world_size, hyper_dev);
     NGP_LAUNCHED("loss_scale_update_kernel");
+    return 0;
+}
+
+int ngp_step_reset(int32_t* march_counter2, float* loss_sum, int32_t* found_inf, int32_t* batch_counter, void* stream) {
+    step_reset_kernel<<<1, 32, 0, ngp::as_stream(stream)>>>(march_counter2, loss_sum, found_inf, batch_counter);
+    NGP_LAUNCHED("step_reset_kernel");
     return 0;
 }
 

@@ -139,7 +139,6 @@ class StaticTrainStep:
         check(L.ngp_ray_aabb_intersect(_p(self.rays_o), _p(self.rays_d), float(m.scale), _p(self.hits), n, st))
         # single-pass march: every ray reserves its rows with one atomic (row order across rays is arbitrary, as
         # in the reference's atomics at ray_march.py:76-81; the module API keeps the deterministic two-pass layout)
-        self.counter.zero_()
         check(L.ngp_raymarching_frame(_p(self.rays_o), _p(self.rays_d), _p(self.hits), _p(self.noise), _p(bits),
                                       m.cascades, m.grid_size, float(m.scale), self.esf, self.max_samples,
                                       _p(self.counter), _p(self.rays_a), _p(self.xyzs), _p(self.dirs),
@@ -154,7 +153,6 @@ class StaticTrainStep:
         check(L.ngp_mlp_fwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.sig), _p(self.rgbs),
                                 cap, nd, st))
         # composite forward + background + MSE + composite backward in one launch (per-ray work)
-        self.loss_sum.zero_()
         bg = 1.0 if self.esf == 0 else 0.0
         check(L.ngp_ray_head_fused(_p(self.sig), _p(self.rgbs), F16, _p(self.deltas), _p(self.rays_a), _p(self.gt), bg,
                                    float(self.tr.loss_scale), _p(self.scale_state) if self.dynamic_loss_scale else None,
@@ -170,18 +168,14 @@ class StaticTrainStep:
     def _enqueue_optimizer(self):
         L, tr, st = load(), self.tr, self._st()
         fg = tr.flat_grad
-        tr.found_inf.zero_()
         check(L.ngp_check_finite(_p(fg), fg.numel(), _p(tr.found_inf), st))
         # inv_scale: static (host constant) or the device value maintained by ngp_loss_scale_update (-1 sentinel)
         inv = -1.0 if self.dynamic_loss_scale else parallel.inv_grad_scale(tr.loss_scale, tr.world_size)
         check(L.ngp_adam_hyper_update(_p(self.step_dev), tr.lr0, tr.lr0 / 30, tr.max_steps, tr.betas[0], tr.betas[1],
                                       inv, _p(self.hyper), st))
-        enc = self.model.pos_encoder
-        for p, (off, s) in zip(tr.params, tr.slices):
-            shadow = tr._shadow if (tr._shadow is not None and p is enc.hash_table) else None
-            check(L.ngp_adam_step_dyn(_p(p.data), _p(fg[off:off + s]), _p(tr.exp_avg[off:off + s]),
-                                      _p(tr.exp_avg_sq[off:off + s]), _p(shadow), _p(tr.found_inf), _p(self.hyper),
-                                      tr.betas[0], tr.betas[1], tr.eps, 1, s, st))
+        # one launch over [hash table | MLP weights] (the trainer keeps parameters, moments and gradients flat)
+        check(L.ngp_adam_step_dyn(_p(tr.flat_param), _p(fg), _p(tr.exp_avg), _p(tr.exp_avg_sq), _p(tr._shadow_full),
+                                  _p(tr.found_inf), _p(self.hyper), tr.betas[0], tr.betas[1], tr.eps, 1, fg.numel(), st))
         if self.dynamic_loss_scale:  # GradScaler.update(): adjusts the scale used by the NEXT step
             check(L.ngp_loss_scale_update(_p(self.scale_state), _p(tr.found_inf), 2.0, 0.5, 2000, float(tr.world_size),
                                           _p(self.hyper), st))
@@ -193,7 +187,6 @@ class StaticTrainStep:
                                           src["poses"].shape[0], src["dirs"].shape[0], None, None, src["fixed_img"],
                                           src["seed"], _p(self.sample_step), 0, _p(self.rays_o), _p(self.rays_d),
                                           _p(self.gt), _p(self.noise), None, None, self.n, self._st()))
-        self.sample_step.add_(1)   # own batch counter: step_dev moves with the optimizer, which may run a step late
 
     def _enqueue_update(self):
         if self.tr.world_size > 1:
@@ -203,6 +196,10 @@ class StaticTrainStep:
     def _enqueue(self, sampled=False, mode="sync"):
         if sampled:
             self._enqueue_sampler()
+        # march counter, loss accumulator, found_inf <- 0 and (own batch counter: step_dev moves with the optimizer,
+        # which may run a step late) sample_step += 1, in one launch
+        check(load().ngp_step_reset(_p(self.counter), _p(self.loss_sum), _p(self.tr.found_inf),
+                                    _p(self.sample_step) if sampled else None, self._st()))
         if mode == "steady":
             # optimizer of the PREVIOUS step beside this step's ray_aabb + marching.  The marching branch runs on
             # a high-priority stream (the priority is kept by the captured kernel nodes): its latency-bound warps
@@ -225,7 +222,7 @@ class StaticTrainStep:
         tr = self.tr
         keep = [p.data.clone() for p in tr.params] + [tr.exp_avg.clone(), tr.exp_avg_sq.clone(), self.step_dev.clone()]
         scale_keep, hyper_keep, sample_keep = self.scale_state.clone(), self.hyper.clone(), self.sample_step.clone()
-        shadow = None if tr._shadow is None else tr._shadow.clone()
+        shadow = None if tr._shadow_full is None else tr._shadow_full.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -249,7 +246,7 @@ class StaticTrainStep:
         self.sample_step.copy_(sample_keep)
         tr.flat_grad.zero_()
         if shadow is not None:
-            tr._shadow.copy_(shadow)
+            tr._shadow_full.copy_(shadow)
         self._graphs[(sampled, mode)], self._kernels[(sampled, mode)] = graph, kernels
 
     # ---------------------------------------------------------------------------------------------
@@ -279,6 +276,7 @@ class StaticTrainStep:
         """Overlap mode: apply the optimizer update of the last step now (before anything reads the parameters:
         update_density_grid, rendering, checkpoints).  No-op otherwise."""
         if self.pending:
+            self.tr.found_inf.zero_()
             self._enqueue_update()
             self.pending = False
             if self.tr._shadow is not None:

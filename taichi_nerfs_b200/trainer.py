@@ -43,6 +43,9 @@ class NGPTrainer:
         pad = [(-s) % 4 for s in sizes]  # keep every slice 16-byte aligned for the float4 Adam kernel
         total = sum(s + q for s, q in zip(sizes, pad))
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        # parameters live in one flat buffer as well (each nn.Parameter becomes a view of it, state_dict is
+        # unchanged), so the fused Adam is ONE launch over [hash table | MLP weights]
+        self.flat_param = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
         self.slices = []
@@ -50,14 +53,20 @@ class NGPTrainer:
         for p, s, q in zip(self.params, sizes, pad):
             self.slices.append((off, s))
             p.grad = self.flat_grad[off:off + s].view_as(p)  # autograd accumulates straight into the flat buffer
+            with torch.no_grad():
+                self.flat_param[off:off + s].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + s].view_as(p)
             off += s + q
             if p is getattr(model.pos_encoder, 'hash_table', None):
                 model.pos_encoder.grad_sink = self.flat_grad[off - s - q:off - q]
         self.found_inf = torch.zeros(1, device=dev, dtype=torch.int32)
-        self._shadow = None
+        self._shadow = self._shadow_full = None
         enc = model.pos_encoder
         if hasattr(enc, "adopt_shadow"):
-            self._shadow = enc.hash_table.detach().to(torch.float16).contiguous()
+            assert self.params[0] is enc.hash_table, "the hash table must be the first parameter"
+            # fp16 copy of the whole flat buffer, rewritten by the Adam pass; the encoder reads its first slice
+            self._shadow_full = self.flat_param.to(torch.float16)
+            self._shadow = self._shadow_full[:enc.hash_table.numel()]
             enc.adopt_shadow(self._shadow)
 
     # cosine annealing to lr/30 (train.py:159-163, CosineAnnealingLR(T_max=max_steps, eta_min=lr/30))
@@ -82,14 +91,11 @@ class NGPTrainer:
         ops.check_finite(self.flat_grad, self.found_inf)  # after the sum: identical on every rank
         lr = self.lr_at(self.step_count - 1)
         inv = parallel.inv_grad_scale(self.loss_scale, self.world_size)
-        enc = self.model.pos_encoder
-        for p, (off, s) in zip(self.params, self.slices):
-            shadow = self._shadow if (self._shadow is not None and p is enc.hash_table) else None
-            ops.adam_step(p.data, self.flat_grad[off:off + s], self.exp_avg[off:off + s], self.exp_avg_sq[off:off + s],
-                          lr, self.step_count, self.betas[0], self.betas[1], self.eps, inv, param_f16=shadow,
-                          found_inf=self.found_inf, zero_grad=True)
-            if shadow is not None:
-                enc.adopt_shadow(shadow)
+        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr, self.step_count,
+                      self.betas[0], self.betas[1], self.eps, inv, param_f16=self._shadow_full,
+                      found_inf=self.found_inf, zero_grad=True)
+        if self._shadow is not None:
+            self.model.pos_encoder.adopt_shadow(self._shadow)
 
     def step(self, rays_o, rays_d, rgb_gt, exp_step_factor=0.0, extra_loss=None):
         loss, results = self.forward_backward(rays_o, rays_d, rgb_gt, exp_step_factor, extra_loss)
