@@ -158,8 +158,8 @@ int ngp_hash_encode_bwd_dyn(const float* xyz, const void* dout, int dout_dtype, 
                             float* grad_table, int64_t n_max, const int32_t* n_dev, const float* aabb6,
                             void* stream);
 int ngp_mlp_fwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
-                    void* rgbs_f16, int64_t n_max, const int32_t* n_dev, void* stream);
-int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w,
+                    void* rgbs_f16, void* save, int64_t n_max, const int32_t* n_dev, void* stream);
+int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
                     const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n_max,
                     const int32_t* n_dev, void* stream);
 /* Adam with the per-step scalars in device memory: hyper_dev = {lr/(1-beta1^t), sqrt(1-beta2^t), inv_scale}
@@ -200,8 +200,11 @@ int ngp_dir_encode(const float* dirs, float* out, int64_t n, void* stream);
  * MLP.forward :369-380 under torch.autocast(fp16) (train.py:177):
  *   emb [n,32] (fp16 or fp32), dirs [n,3] fp32 (un-normalised)
  *   -> sigmas [n] fp32, rgbs [n,3] fp16, h [n,16] fp16 (geometry feature)
- * With `save` != NULL the activations needed by the backward are stored there
- * (ngp_mlp_save_bytes(n) bytes). */
+ * With `save` != NULL (ngp_mlp_save_bytes(n) = 40 n bytes, 16-byte aligned) the forward also stores what
+ * torch.autograd would keep for the backward and is cheap to keep: h [n,16] fp16 and the fp16 sigmoid output
+ * [n,4]; the backward given the same `save` then restarts from h (8 MMA rounds per tile instead of 10) and
+ * forms sigmoid' from the saved output exactly as torch's sigmoid_backward does.  save == NULL: the backward
+ * recomputes everything from (emb, dirs). */
 int64_t ngp_mlp_save_bytes(int64_t n);
 int ngp_mlp_fwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w,
                 float* sigmas, void* rgbs_f16, void* save, int64_t n, void* stream);

@@ -42,9 +42,9 @@ def main():
     w = W(*[t.data_ptr() for t in ws])
     sig = torch.empty(n, device=dev)
     rgb = torch.empty(n, 3, device=dev, dtype=torch.float16)
-    lib.ngp_mlp_fwd_dyn.argtypes = [vp, C.c_int, vp, C.POINTER(W), vp, vp, i64, vp, vp]
+    lib.ngp_mlp_fwd_dyn.argtypes = [vp, C.c_int, vp, C.POINTER(W), vp, vp, vp, i64, vp, vp]
     for _ in range(3):
-        rc = lib.ngp_mlp_fwd_dyn(emb.data_ptr(), 1, dirs.data_ptr(), C.byref(w), sig.data_ptr(), rgb.data_ptr(), n, None,
+        rc = lib.ngp_mlp_fwd_dyn(emb.data_ptr(), 1, dirs.data_ptr(), C.byref(w), sig.data_ptr(), rgb.data_ptr(), None, n, None,
                                  torch.cuda.current_stream().cuda_stream)
         assert rc == 0
     torch.cuda.synchronize()

@@ -26,6 +26,8 @@ namespace {
 constexpr int kTile = 128;          // samples per tile == UMMA M
 constexpr int kRows = 128;          // sample rows per tile == TMEM lanes
 constexpr int kThreads = 256;       // TWO threads per row: warps 0-3 own accumulator columns [0,32), warps 4-7 own [32,64)
+constexpr int kThreadsBwd = 288;    // backward: + warp 8, which only issues MMAs (the 8-MMA weight-gradient batches of a
+                                    // round are issued while warps 0-7 run that round's epilogue)
                                     // (a warp may touch TMEM lanes 32*(warp%4)..+31), halving every epilogue's latency
 constexpr uint32_t kTmemCols = 64;  // fp32 accumulator columns (max N = 64)
 
@@ -186,6 +188,7 @@ __device__ __forceinline__ uint32_t pack_h2_relu(float a, float b) {
 // copy a row-major fp32 weight [rows x K] into the interleaved fp16 operand layout (rows_pad rows)
 __device__ __forceinline__ void stage_weight(uint8_t* smem, const float* __restrict__ w, int rows, int rows_pad, int K) {
     const int kchunks = K / 8;
+    if (threadIdx.x >= kThreads) return;  // the backward's MMA-issue warp does not stage
     for (int c = threadIdx.x; c < rows_pad * kchunks; c += kThreads) {
         const int r = c / kchunks, kc = c % kchunks;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -238,13 +241,23 @@ struct RowIn {
     uint4 e[2];          // this thread's 2 of the row's 4 embedding chunks (16 fp16 values)
     float dx, dy, dz;    // used by hh == 1 (SH)
     float dsig, dr[3];   // backward only, used by hh == 0
+    uint4 hs[2];         // backward with saved activations: h (16 fp16) of this row, used by hh == 0
+    uint2 rgb;           // ... and the forward's fp16 rgb output (3 used)
 };
-template <typename TEmb, bool kBwd>
+// activations saved by the forward for the backward (ngp_mlp_save_bytes): [n_max x 16] fp16 h = sigma-net output,
+// then [n_max x 4] fp16 rgb (the sigmoid output, as torch's sigmoid backward keeps it)
+__device__ __forceinline__ const __half* save_rgb_ptr(const __half* save, int64_t n_max) { return save + n_max * 16; }
+__device__ __forceinline__ __half* save_rgb_ptr(__half* save, int64_t n_max) { return save + n_max * 16; }
+
+template <typename TEmb, bool kBwd, bool kSaved = false>
 __device__ __forceinline__ RowIn load_row(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
                                            const float* __restrict__ dsigmas, const __half* __restrict__ drgbs,
-                                           int64_t i, bool valid, int hh) {
+                                           int64_t i, bool valid, int hh, const __half* __restrict__ save = nullptr,
+                                           int64_t n_max = 0) {
     RowIn r;
     r.e[0] = r.e[1] = make_uint4(0, 0, 0, 0);
+    r.hs[0] = r.hs[1] = make_uint4(0, 0, 0, 0);
+    r.rgb = make_uint2(0, 0);
     r.dx = 0.f; r.dy = 0.f; r.dz = 1.f; r.dsig = 0.f; r.dr[0] = r.dr[1] = r.dr[2] = 0.f;
     if (valid) {
 #pragma unroll
@@ -266,6 +279,11 @@ __device__ __forceinline__ RowIn load_row(const TEmb* __restrict__ emb, const fl
             r.dsig = __ldg(dsigmas + i);
 #pragma unroll
             for (int c = 0; c < 3; ++c) r.dr[c] = __half2float(drgbs[i * 3 + c]);
+            if constexpr (kSaved) {
+                r.hs[0] = __ldg(reinterpret_cast<const uint4*>(save + i * 16));
+                r.hs[1] = __ldg(reinterpret_cast<const uint4*>(save + i * 16) + 1);
+                r.rgb = __ldg(reinterpret_cast<const uint2*>(save_rgb_ptr(save, n_max) + i * 4));
+            }
         }
     }
     return r;
@@ -274,8 +292,8 @@ __device__ __forceinline__ RowIn load_row(const TEmb* __restrict__ emb, const fl
 template <typename TEmb>
 __global__ void __launch_bounds__(kThreads, 4) mlp_fwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
                                                            ngp_mlp_weights w, float* __restrict__ sigmas,
-                                                           __half* __restrict__ rgbs, int64_t n_max,
-                                                           const int32_t* __restrict__ n_dev) {
+                                                           __half* __restrict__ rgbs, __half* __restrict__ save,
+                                                           int64_t n_max, const int32_t* __restrict__ n_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int64_t n = n_dev ? min(n_max, max((int64_t)*n_dev, (int64_t)0)) : n_max;
     const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kRows - 1), hh = tid >> 7;
@@ -364,10 +382,14 @@ __global__ void __launch_bounds__(kThreads, 4) mlp_fwd_kernel(const TEmb* __rest
             const float h0 = __half2float(__float2half_rn(h[0]));
             if (valid) sigmas[i] = expf(h0);
             uint8_t* dst = smem + kBufA;
-            *reinterpret_cast<uint4*>(dst + chunk_off(row, 2, 32)) =
-                make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
-            *reinterpret_cast<uint4*>(dst + chunk_off(row, 3, 32)) =
-                make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
+            const uint4 lo = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+            const uint4 hi = make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 2, 32)) = lo;
+            *reinterpret_cast<uint4*>(dst + chunk_off(row, 3, 32)) = hi;
+            if (save != nullptr && valid) {   // the backward restarts from h instead of recomputing layers 1-2 serially
+                reinterpret_cast<uint4*>(save + i * 16)[0] = lo;
+                reinterpret_cast<uint4*>(save + i * 16)[1] = hi;
+            }
         } else {
             // the direction half, in parallel: SH16((d/|d| + 1)/2)  (networks.py:162-164)
             const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
@@ -439,10 +461,17 @@ __global__ void __launch_bounds__(kThreads, 4) mlp_fwd_kernel(const TEmb* __rest
             float o[16];
             tmem_ld16(tmem_row, o);
             if (valid) {
+                __half out[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float oc = __half2float(__float2half_rn(o[c]));
-                    rgbs[i * 3 + c] = __float2half_rn(1.0f / (1.0f + expf(-oc)));
+                    out[c] = __float2half_rn(1.0f / (1.0f + expf(-oc)));
+                    rgbs[i * 3 + c] = out[c];
+                }
+                if (save != nullptr) {
+                    const __half2 a = __halves2half2(out[0], out[1]), b = __halves2half2(out[2], __float2half_rn(0.0f));
+                    *reinterpret_cast<uint2*>(save_rgb_ptr(save, n_max) + i * 4) =
+                        make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
                 }
             }
         }
@@ -512,15 +541,17 @@ __device__ __forceinline__ void epilogue_relu_bwd(uint32_t tmem_row, const uint8
     }
 }
 
-template <typename TEmb>
-__global__ void __launch_bounds__(kThreads, 2) mlp_bwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
-                                                           ngp_mlp_weights w, const float* __restrict__ dsigmas,
+template <typename TEmb, bool kSaved>
+__global__ void __launch_bounds__(kThreadsBwd, 2) mlp_bwd_kernel(const TEmb* __restrict__ emb, const float* __restrict__ dirs,
+                                                           ngp_mlp_weights w, const __half* __restrict__ save,
+                                                           const float* __restrict__ dsigmas,
                                                            const __half* __restrict__ drgbs, TEmb* __restrict__ demb,
                                                            float* __restrict__ grad_w, int64_t n_max,
                                                            const int32_t* __restrict__ n_dev) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int64_t n = n_dev ? min(n_max, max((int64_t)*n_dev, (int64_t)0)) : n_max;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & (kRows - 1), hh = tid >> 7;
+    const bool worker = tid < kThreads;   // warps 0-7: two threads per tile row; warp 8 (hh == 2): MMA issue only
     const uint32_t bar = smem_u32(smem + kBarBwd);
     const uint32_t bar2 = smem_u32(smem + kBarBwd + 16);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBarBwd + 8);
@@ -559,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_bwd_kernel(const TEmb* __rest
     fence_proxy_async();                       \
     tc_fence_before();                         \
     __syncthreads();                           \
-    if (tid == 0) {                            \
+    if (tid == kThreads) {                     \
         tc_fence_after();                      \
         DX;                                    \
         umma_commit(bar);                      \
@@ -573,35 +604,51 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_bwd_kernel(const TEmb* __rest
 
     bool first = true;  // first tile of this CTA: weight-gradient accumulators start from zero
     const int64_t n_tiles = (n + kTile - 1) / kTile;
-    RowIn cur = load_row<TEmb, true>(emb, dirs, dsigmas, drgbs, (int64_t)blockIdx.x * kTile + row,
-                                     (int64_t)blockIdx.x * kTile + row < n, hh);
+    RowIn cur = load_row<TEmb, true, kSaved>(emb, dirs, dsigmas, drgbs, (int64_t)blockIdx.x * kTile + row,
+                                             worker && (int64_t)blockIdx.x * kTile + row < n, hh, save, n_max);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * kTile + row;
-        const bool valid = i < n;
+        const bool valid = worker && i < n;
 
         // ================= forward recompute =================
+        if (worker) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) *reinterpret_cast<uint4*>(smem + kE + chunk_off(row, hh * 2 + q, 32)) = cur.e[q];
+            for (int q = 0; q < 2; ++q) *reinterpret_cast<uint4*>(smem + kE + chunk_off(row, hh * 2 + q, 32)) = cur.e[q];
+        }
         const float dx = cur.dx, dy = cur.dy, dz = cur.dz, dsig = cur.dsig;  // dirs: hh == 1, dsig/dr: hh == 0
         const float dr[3] = {cur.dr[0], cur.dr[1], cur.dr[2]};
+        [[maybe_unused]] const uint4 hs0 = cur.hs[0], hs1 = cur.hs[1];
+        [[maybe_unused]] const uint2 rgb_saved = cur.rgb;
         {   // prefetch the next tile of this CTA (consumed one iteration later)
             const int64_t in = (tile + gridDim.x) * kTile + row;
-            cur = load_row<TEmb, true>(emb, dirs, dsigmas, drgbs, in, in < n, hh);
+            cur = load_row<TEmb, true, kSaved>(emb, dirs, dsigmas, drgbs, in, worker && in < n, hh, save, n_max);
+        }
+        float h0 = 0.0f;
+        if constexpr (kSaved) {
+            // X3 = [SH | h] straight from the saved h: layers 2 and 5 are not recomputed (8 MMA rounds instead of 10)
+            if (hh == 0) {
+                const __half2 h01 = *reinterpret_cast<const __half2*>(&hs0.x);
+                h0 = __low2float(h01);
+                *reinterpret_cast<uint4*>(smem + kX3 + chunk_off(row, 2, 32)) = hs0;
+                *reinterpret_cast<uint4*>(smem + kX3 + chunk_off(row, 3, 32)) = hs1;
+            }
         }
         NGP_ROUND(issue_layer_mma(tmem_base, aE, aW1, 32, 64))          // H1 = relu(E W1^T)
-        epilogue_hidden(tmem_row, smem + kH1, row, hh);
-        NGP_ROUND(issue_layer_mma(tmem_base, aH1, aW2, 64, 16))         // h = H1 W2^T
-        float h0 = 0.0f;
-        if (hh == 0) {
-            float h[16];
-            tmem_ld16(tmem_row, h);
-            h0 = __half2float(__float2half_rn(h[0]));
-            uint8_t* dst = smem + kX3;
-            *reinterpret_cast<uint4*>(dst + chunk_off(row, 2, 32)) =
-                make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
-            *reinterpret_cast<uint4*>(dst + chunk_off(row, 3, 32)) =
-                make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
-        } else {
+        if (worker) epilogue_hidden(tmem_row, smem + kH1, row, hh);
+        if constexpr (!kSaved) {
+            NGP_ROUND(issue_layer_mma(tmem_base, aH1, aW2, 64, 16))     // h = H1 W2^T
+            if (hh == 0) {
+                float h[16];
+                tmem_ld16(tmem_row, h);
+                h0 = __half2float(__float2half_rn(h[0]));
+                uint8_t* dst = smem + kX3;
+                *reinterpret_cast<uint4*>(dst + chunk_off(row, 2, 32)) =
+                    make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+                *reinterpret_cast<uint4*>(dst + chunk_off(row, 3, 32)) =
+                    make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
+            }
+        }
+        if (hh == 1) {
             const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
             float e[16];
             sh16((dx * inv + 1.0f) / 2.0f, (dy * inv + 1.0f) / 2.0f, (dz * inv + 1.0f) / 2.0f, e);
@@ -612,24 +659,36 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_bwd_kernel(const TEmb* __rest
                 make_uint4(pack_h2(e[8], e[9]), pack_h2(e[10], e[11]), pack_h2(e[12], e[13]), pack_h2(e[14], e[15]));
         }
         NGP_ROUND(issue_layer_mma(tmem_base, aX3, aW3, 32, 64))         // H3 = relu(X3 W3^T)
-        epilogue_hidden(tmem_row, smem + kH3, row, hh);
+        if (worker) epilogue_hidden(tmem_row, smem + kH3, row, hh);
         NGP_ROUND(issue_layer_mma(tmem_base, aH3, aW4, 64, 64))         // H4 = relu(H3 W4^T)
-        epilogue_hidden(tmem_row, smem + kH4, row, hh);
-        NGP_ROUND(issue_layer_mma(tmem_base, aH4, aW5, 64, 16))         // o = H4 W5^T
+        if (worker) epilogue_hidden(tmem_row, smem + kH4, row, hh);
+        if constexpr (!kSaved) {
+            NGP_ROUND(issue_layer_mma(tmem_base, aH4, aW5, 64, 16))     // o = H4 W5^T
+        }
         if (hh == 0) {
             // dL/do = dL/drgb * rgb (1 - rgb), rounded to fp16 like the autocast graph
-            float o[16];
-            tmem_ld16(tmem_row, o);
+            float rgbv[3];
+            if constexpr (kSaved) {   // torch's sigmoid backward also uses the saved fp16 output
+                const __half2 a = *reinterpret_cast<const __half2*>(&rgb_saved.x);
+                const __half2 b = *reinterpret_cast<const __half2*>(&rgb_saved.y);
+                rgbv[0] = __low2float(a);
+                rgbv[1] = __high2float(a);
+                rgbv[2] = __low2float(b);
+            } else {
+                float o[16];
+                tmem_ld16(tmem_row, o);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float oc = __half2float(__float2half_rn(o[c]));
+                    rgbv[c] = __half2float(__float2half_rn(1.0f / (1.0f + expf(-oc))));
+                }
+            }
             float d_o[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float oc = __half2float(__float2half_rn(o[c]));
-                const float rgb = __half2float(__float2half_rn(1.0f / (1.0f + expf(-oc))));
-                d_o[c] = dr[c] * rgb * (1.0f - rgb);
-            }
+            for (int c = 0; c < 3; ++c) d_o[c] = dr[c] * rgbv[c] * (1.0f - rgbv[c]);
             *reinterpret_cast<uint4*>(smem + kDO + chunk_off(row, 0, 16)) =
                 make_uint4(pack_h2(d_o[0], d_o[1]), pack_h2(d_o[2], 0.0f), 0u, 0u);
-        } else {
+        } else if (hh == 1) {
             *reinterpret_cast<uint4*>(smem + kDO + chunk_off(row, 1, 16)) = make_uint4(0u, 0u, 0u, 0u);
         }
 
@@ -639,13 +698,13 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_bwd_kernel(const TEmb* __rest
             issue_gemm(tmem_base, op_kmajor(aDO, 16), op_mnmajor(aW5, 64), 1, idesc_full(128, 64, 0, 1), false),
             issue_gemm(tmem_base + kColDW5T, op_mnmajor(aH4, 64), op_mnmajor(aDO, 16), 8, idesc_full(64, 16, 1, 1), !first),
             false)
-        epilogue_relu_bwd(tmem_row, smem + kH4, smem + kDH4, row, hh);
+        if (worker) epilogue_relu_bwd(tmem_row, smem + kH4, smem + kDH4, row, hh);
         // R2: dH3pre = dH4 W4 ;  dW4 += dH4^T H3
         NGP_ROUND2(
             issue_gemm(tmem_base, op_kmajor(aDH4, 64), op_mnmajor(aW4, 64), 4, idesc_full(128, 64, 0, 1), false),
             issue_gemm(tmem_base + kColDW4, op_mnmajor(aDH4, 64), op_mnmajor(aH3, 64), 8, idesc_full(64, 64, 1, 1), !first),
             false)
-        epilogue_relu_bwd(tmem_row, smem + kH3, smem + kH4, row, hh);      // dH3 -> H4's buffer (H4 is dead)
+        if (worker) epilogue_relu_bwd(tmem_row, smem + kH3, smem + kH4, row, hh);      // dH3 -> H4's buffer (H4 is dead)
         // R3: dX3 = dH3 W3 ;  dW3 += dH3^T X3
         NGP_ROUND2(
             issue_gemm(tmem_base, op_kmajor(aH4, 64), op_mnmajor(aW3, 32), 4, idesc_full(128, 32, 0, 1), false),
@@ -667,13 +726,13 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_bwd_kernel(const TEmb* __rest
             issue_gemm(tmem_base, op_kmajor(aDH, 16), op_mnmajor(aW2, 64), 1, idesc_full(128, 64, 0, 1), false),
             issue_gemm(tmem_base + kColDW2T, op_mnmajor(aH1, 64), op_mnmajor(aDH, 16), 8, idesc_full(64, 16, 1, 1), !first),
             false)
-        epilogue_relu_bwd(tmem_row, smem + kH1, smem + kH3, row, hh);      // dH1 -> H3's buffer (H3 is dead)
+        if (worker) epilogue_relu_bwd(tmem_row, smem + kH1, smem + kH3, row, hh);      // dH1 -> H3's buffer (H3 is dead)
         // R5: dE = dH1 W1 ;  dW1 += dH1^T E
         NGP_ROUND2(
             issue_gemm(tmem_base, op_kmajor(aH3, 64), op_mnmajor(aW1, 32), 4, idesc_full(128, 32, 0, 1), false),
             issue_gemm(tmem_base + kColDW1, op_mnmajor(aH3, 64), op_mnmajor(aE, 32), 8, idesc_full(64, 32, 1, 1), !first),
             true)
-        {
+        if (worker) {
             const int g = hh;  // columns [16*hh, 16*hh+16) of dE
             float v[16];
             tmem_ld16(tmem_row + g * 16, v);
@@ -742,12 +801,13 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_bwd_kernel(const TEmb* __rest
     if (warp == 0) tmem_dealloc(tmem_base, kTmemColsBwd);
 }
 
-template <typename TEmb>
-int launch_bwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, const float* dsigmas, const void* drgbs,
-               void* demb, float* grad_w, int64_t n, const int32_t* n_dev, cudaStream_t st) {
+template <typename TEmb, bool kSaved>
+int launch_bwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, const void* save, const float* dsigmas,
+               const void* drgbs, void* demb, float* grad_w, int64_t n, const int32_t* n_dev, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel<TEmb>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesBwd);
+        cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel<TEmb, kSaved>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSmemBytesBwd);
         if (e != cudaSuccess) {
             ngp::set_error("mlp_bwd_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return (int)e;
@@ -757,15 +817,16 @@ int launch_bwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, con
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int64_t max_ctas = (int64_t)ngp::sm_count() * 2;  // 108 KB smem + 256 TMEM columns per CTA
     const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
-    mlp_bwd_kernel<TEmb><<<grid, kThreads, kSmemBytesBwd, st>>>((const TEmb*)emb, dirs, *w, dsigmas, (const __half*)drgbs,
-                                                               (TEmb*)demb, grad_w, n, n_dev);
+    mlp_bwd_kernel<TEmb, kSaved><<<grid, kThreadsBwd, kSmemBytesBwd, st>>>((const TEmb*)emb, dirs, *w, (const __half*)save,
+                                                                       dsigmas, (const __half*)drgbs, (TEmb*)demb,
+                                                                       grad_w, n, n_dev);
     NGP_LAUNCHED("mlp_bwd_kernel");
     return 0;
 }
 
 template <typename TEmb>
-int launch_fwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, float* sigmas, void* rgbs, int64_t n,
-               const int32_t* n_dev, cudaStream_t st) {
+int launch_fwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, float* sigmas, void* rgbs, void* save,
+               int64_t n, const int32_t* n_dev, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel<TEmb>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -778,7 +839,8 @@ int launch_fwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, flo
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int64_t max_ctas = (int64_t)ngp::sm_count() * 4;  // 52 KB smem + 64 TMEM columns per CTA
     const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
-    mlp_fwd_kernel<TEmb><<<grid, kThreads, kSmemBytes, st>>>((const TEmb*)emb, dirs, *w, sigmas, (__half*)rgbs, n, n_dev);
+    mlp_fwd_kernel<TEmb><<<grid, kThreads, kSmemBytes, st>>>((const TEmb*)emb, dirs, *w, sigmas, (__half*)rgbs,
+                                                            (__half*)save, n, n_dev);
     NGP_LAUNCHED("mlp_fwd_kernel");
     return 0;
 }
@@ -794,55 +856,60 @@ extern "C" int ngp_debug_mlp_trace(long long* out_host) {
 extern "C" {
 
 int64_t ngp_mlp_save_bytes(int64_t n) {
-    (void)n;
-    return 0;  // the backward recomputes the activations from (emb, dirs): nothing is saved
+    // [n x 16] fp16 h (sigma-net output) + [n x 4] fp16 rgb (3 used): with them the backward skips layers 2 and 5
+    return n > 0 ? n * 40 : 0;
 }
 
-int ngp_mlp_fwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
-                void* rgbs_f16, void* save, int64_t n, void* stream) {
-    (void)save;
-    return ngp_mlp_fwd_dyn(emb, emb_dtype, dirs, w, sigmas, rgbs_f16, n, nullptr, stream);
-}
-
-int ngp_mlp_fwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
-                    void* rgbs_f16, int64_t n, const int32_t* n_dev, void* stream) {
-    NGP_REQUIRE(n >= 0, "negative n");
+static int check_mlp_args(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w) {
     NGP_REQUIRE(emb_dtype == NGP_F32 || emb_dtype == NGP_F16, "bad dtype");
-    if (n == 0) return 0;
-    NGP_REQUIRE(emb && dirs && w && sigmas && rgbs_f16, "null pointer");
+    NGP_REQUIRE(emb && dirs && w, "null pointer");
     NGP_REQUIRE(w->w1 && w->w2 && w->w3 && w->w4 && w->w5, "null weight pointer");
     NGP_REQUIRE((reinterpret_cast<uintptr_t>(emb) & 15) == 0, "emb must be 16-byte aligned");
     const uintptr_t wal = reinterpret_cast<uintptr_t>(w->w1) | reinterpret_cast<uintptr_t>(w->w2) |
                           reinterpret_cast<uintptr_t>(w->w3) | reinterpret_cast<uintptr_t>(w->w4) |
                           reinterpret_cast<uintptr_t>(w->w5);
     NGP_REQUIRE((wal & 15) == 0, "weights must be 16-byte aligned");
+    return 0;
+}
+
+int ngp_mlp_fwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
+                void* rgbs_f16, void* save, int64_t n, void* stream) {
+    return ngp_mlp_fwd_dyn(emb, emb_dtype, dirs, w, sigmas, rgbs_f16, save, n, nullptr, stream);
+}
+
+int ngp_mlp_fwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
+                    void* rgbs_f16, void* save, int64_t n, const int32_t* n_dev, void* stream) {
+    NGP_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return 0;
+    if (int rc = check_mlp_args(emb, emb_dtype, dirs, w)) return rc;
+    NGP_REQUIRE(sigmas && rgbs_f16, "null pointer");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(save) & 15) == 0, "save must be 16-byte aligned");
     cudaStream_t st = ngp::as_stream(stream);
-    if (emb_dtype == NGP_F16) return launch_fwd<__half>(emb, dirs, w, sigmas, rgbs_f16, n, n_dev, st);
-    return launch_fwd<float>(emb, dirs, w, sigmas, rgbs_f16, n, n_dev, st);
+    if (emb_dtype == NGP_F16) return launch_fwd<__half>(emb, dirs, w, sigmas, rgbs_f16, save, n, n_dev, st);
+    return launch_fwd<float>(emb, dirs, w, sigmas, rgbs_f16, save, n, n_dev, st);
 }
 
 int ngp_mlp_bwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
                 const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n, void* stream) {
-    (void)save;
-    return ngp_mlp_bwd_dyn(emb, emb_dtype, dirs, w, dsigmas, drgbs_f16, demb, grad_w, n, nullptr, stream);
+    return ngp_mlp_bwd_dyn(emb, emb_dtype, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, nullptr, stream);
 }
 
-int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const float* dsigmas,
-                    const void* drgbs_f16, void* demb, float* grad_w, int64_t n, const int32_t* n_dev, void* stream) {
+int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
+                    const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n,
+                    const int32_t* n_dev, void* stream) {
     NGP_REQUIRE(n >= 0, "negative n");
-    NGP_REQUIRE(emb_dtype == NGP_F32 || emb_dtype == NGP_F16, "bad dtype");
     if (n == 0) return 0;
-    NGP_REQUIRE(emb && dirs && w && dsigmas && drgbs_f16 && demb && grad_w, "null pointer");
-    NGP_REQUIRE(w->w1 && w->w2 && w->w3 && w->w4 && w->w5, "null weight pointer");
-    NGP_REQUIRE(((reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(demb)) & 15) == 0,
-                "emb/demb must be 16-byte aligned");
-    const uintptr_t wal = reinterpret_cast<uintptr_t>(w->w1) | reinterpret_cast<uintptr_t>(w->w2) |
-                          reinterpret_cast<uintptr_t>(w->w3) | reinterpret_cast<uintptr_t>(w->w4) |
-                          reinterpret_cast<uintptr_t>(w->w5);
-    NGP_REQUIRE((wal & 15) == 0, "weights must be 16-byte aligned");
+    if (int rc = check_mlp_args(emb, emb_dtype, dirs, w)) return rc;
+    NGP_REQUIRE(dsigmas && drgbs_f16 && demb && grad_w, "null pointer");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(demb) & 15) == 0, "demb must be 16-byte aligned");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(save) & 15) == 0, "save must be 16-byte aligned");
     cudaStream_t st = ngp::as_stream(stream);
-    if (emb_dtype == NGP_F16) return launch_bwd<__half>(emb, dirs, w, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st);
-    return launch_bwd<float>(emb, dirs, w, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st);
+    if (emb_dtype == NGP_F16) {
+        return save ? launch_bwd<__half, true>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st)
+                    : launch_bwd<__half, false>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st);
+    }
+    return save ? launch_bwd<float, true>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st)
+                : launch_bwd<float, false>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st);
 }
 
 }  // extern "C"

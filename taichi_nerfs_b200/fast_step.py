@@ -54,6 +54,7 @@ class StaticTrainStep:
         self.emb, self.demb = z(C_, 32, dtype=edt), z(C_, 32, dtype=edt)
         self.sig, self.dsig = z(C_), z(C_)
         self.rgbs, self.drgbs = z(C_, 3, dtype=torch.float16), z(C_, 3, dtype=torch.float16)
+        self.mlp_save = z(int(load().ngp_mlp_save_bytes(C_)), dtype=torch.uint8)   # h + fp16 rgb kept for the backward
         # compositing / loss
         self.total, self.opacity, self.depth, self.rgb = z(self.n, dtype=i32), z(self.n), z(self.n), z(self.n, 3)
         self.ws = z(C_)
@@ -151,7 +152,7 @@ class StaticTrainStep:
         check(L.ngp_hash_encode_fwd_dyn(_p(self.xyzs), _p(self._table()), C.byref(self._clayout), _p(self.emb), tag,
                                         cap, nd, self.aabb6, st))
         check(L.ngp_mlp_fwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.sig), _p(self.rgbs),
-                                cap, nd, st))
+                                _p(self.mlp_save), cap, nd, st))
         # composite forward + background + MSE + composite backward in one launch (per-ray work)
         bg = 1.0 if self.esf == 0 else 0.0
         check(L.ngp_ray_head_fused(_p(self.sig), _p(self.rgbs), F16, _p(self.deltas), _p(self.rays_a), _p(self.gt), bg,
@@ -160,8 +161,8 @@ class StaticTrainStep:
                                    _p(self.drgbs), n, st))
         fg = self.tr.flat_grad
         gw = fg[self.P:self.P + 9408]
-        check(L.ngp_mlp_bwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.dsig), _p(self.drgbs),
-                                _p(self.demb), _p(gw), cap, nd, st))
+        check(L.ngp_mlp_bwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.mlp_save), _p(self.dsig),
+                                _p(self.drgbs), _p(self.demb), _p(gw), cap, nd, st))
         check(L.ngp_hash_encode_bwd_dyn(_p(self.xyzs), _p(self.demb), tag, C.byref(self._clayout), _p(fg), cap, nd,
                                         self.aabb6, st))
 

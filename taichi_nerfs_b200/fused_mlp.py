@@ -31,19 +31,23 @@ class _FusedMLP(torch.autograd.Function):
         emb = emb.contiguous()
         dirs = dirs.float().contiguous()
         ws = [w.detach().float().contiguous() for w in (w1, w2, w3, w4, w5)]
-        sigmas, rgbs = ops.mlp_fwd(emb, dirs, ws)
-        ctx.save_for_backward(emb, dirs, *ws)
+        need_bwd = any(ctx.needs_input_grad)
+        if need_bwd:   # keep h + the fp16 sigmoid output (40 B/sample): the backward then skips two serial layers
+            sigmas, rgbs, save = ops.mlp_fwd(emb, dirs, ws, with_save=True)
+            ctx.save_for_backward(emb, dirs, save, *ws)
+        else:
+            sigmas, rgbs = ops.mlp_fwd(emb, dirs, ws)
         return sigmas, rgbs
 
     @staticmethod
     def backward(ctx, d_sigmas, d_rgbs):
-        emb, dirs, *ws = ctx.saved_tensors
+        emb, dirs, save, *ws = ctx.saved_tensors
         n = emb.shape[0]
         if d_sigmas is None:
             d_sigmas = torch.zeros(n, device=emb.device, dtype=torch.float32)
         if d_rgbs is None:
             d_rgbs = torch.zeros(n, 3, device=emb.device, dtype=torch.float16)
-        demb, gw = ops.mlp_bwd(emb, dirs, ws, d_sigmas, d_rgbs)
+        demb, gw = ops.mlp_bwd(emb, dirs, ws, d_sigmas, d_rgbs, save=save)
         grads = [g.view(s) for g, s in zip(torch.split(gw, _SPLITS), _SHAPES)]
         return (demb if ctx.needs_input_grad[0] else None, None, *grads)
 

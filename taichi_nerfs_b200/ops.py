@@ -284,8 +284,9 @@ def _mlp_weights(ws):
     return _lib.MlpWeights(*[k.data_ptr() for k in keep]), keep
 
 
-def mlp_fwd(emb, dirs, ws):
-    """emb [n,32] fp16/fp32, dirs [n,3] fp32 (un-normalised) -> sigmas [n] fp32, rgbs [n,3] fp16."""
+def mlp_fwd(emb, dirs, ws, with_save=False):
+    """emb [n,32] fp16/fp32, dirs [n,3] fp32 (un-normalised) -> sigmas [n] fp32, rgbs [n,3] fp16
+    [, save: the activations the backward restarts from (ngp_mlp_save_bytes(n) bytes)]."""
     _need_cuda(emb, dirs)
     n = emb.shape[0]
     emb = emb.contiguous()
@@ -293,13 +294,17 @@ def mlp_fwd(emb, dirs, ws):
     st, keep = _mlp_weights(ws)
     sig = torch.empty(n, device=emb.device, dtype=torch.float32)
     rgb = torch.empty(n, 3, device=emb.device, dtype=torch.float16)
-    check(load().ngp_mlp_fwd(_ptr(emb), _tag(emb), _ptr(d), C.byref(st), _ptr(sig), _ptr(rgb), None, n, _stream()),
+    save = None
+    if with_save:
+        save = torch.empty(max(int(load().ngp_mlp_save_bytes(n)), 16), device=emb.device, dtype=torch.uint8)
+    check(load().ngp_mlp_fwd(_ptr(emb), _tag(emb), _ptr(d), C.byref(st), _ptr(sig), _ptr(rgb), _ptr(save), n, _stream()),
           "mlp_fwd")
-    return sig, rgb
+    return (sig, rgb, save) if with_save else (sig, rgb)
 
 
-def mlp_bwd(emb, dirs, ws, dsigmas, drgbs):
-    """-> demb [n,32] (emb dtype), grad_w fp32 [9408] in the order w1|w2|w3|w4|w5."""
+def mlp_bwd(emb, dirs, ws, dsigmas, drgbs, save=None):
+    """-> demb [n,32] (emb dtype), grad_w fp32 [9408] in the order w1|w2|w3|w4|w5.  ``save`` = the buffer returned
+    by mlp_fwd(..., with_save=True) on the same inputs (None: everything is recomputed from emb / dirs)."""
     _need_cuda(emb, dirs, dsigmas, drgbs)
     n = emb.shape[0]
     emb = emb.contiguous()
@@ -307,7 +312,7 @@ def mlp_bwd(emb, dirs, ws, dsigmas, drgbs):
     st, keep = _mlp_weights(ws)
     demb = torch.empty(n, 32, device=emb.device, dtype=emb.dtype)
     gw = torch.zeros(9408, device=emb.device, dtype=torch.float32)
-    check(load().ngp_mlp_bwd(_ptr(emb), _tag(emb), _ptr(d), C.byref(st), None, _ptr(_f32c(dsigmas)),
+    check(load().ngp_mlp_bwd(_ptr(emb), _tag(emb), _ptr(d), C.byref(st), _ptr(save), _ptr(_f32c(dsigmas)),
                              _ptr(drgbs.to(torch.float16).contiguous()), _ptr(demb), _ptr(gw), n, _stream()),
           "mlp_bwd")
     return demb, gw

@@ -137,7 +137,11 @@ def test_fullsize_mlp_matches_oracle(ops, oracle, march):
     dsig = (rng.standard_normal(S) * 1e-2).astype(np.float32)
     drgb = (rng.standard_normal((S, 3)) * 1e-2).astype(np.float16)
     demb_ref, gw_ref = oracle.mlp_bwd(emb, march["dirs"], ws, dsig, drgb)
-    demb, gw = ops.mlp_bwd(T(emb), T(march["dirs"]), [T(w) for w in ws], T(dsig), T(drgb))
+    _, _, save = ops.mlp_fwd(T(emb), T(march["dirs"]), [T(w) for w in ws], with_save=True)
+    demb, gw = ops.mlp_bwd(T(emb), T(march["dirs"]), [T(w) for w in ws], T(dsig), T(drgb), save=save)
+    demb2, gw2 = ops.mlp_bwd(T(emb), T(march["dirs"]), [T(w) for w in ws], T(dsig), T(drgb))     # recompute variant
+    assert float((demb.float() - demb2.float()).abs().max()) <= 2e-3 * float(demb2.float().abs().max())
+    assert float((gw - gw2).abs().max()) <= 2e-3 * float(gw2.abs().max())
     demb, gw = N(demb).astype(np.float32), N(gw)
     scale = np.abs(demb_ref.astype(np.float32)).max()
     assert np.abs(demb - demb_ref.astype(np.float32)).max() <= 5e-3 * scale

@@ -361,9 +361,10 @@ def test_adam_fused(ops, oracle, n):
     assert np.array_equal(N(gp), before)
 
 
+@pytest.mark.parametrize("saved", [False, True])
 @pytest.mark.parametrize("emb_half", [True, False])
 @pytest.mark.parametrize("n", [1, 128, 5000, 40000])
-def test_mlp_bwd_tcgen05_matches_oracle(ops, oracle, emb_half, n):
+def test_mlp_bwd_tcgen05_matches_oracle(ops, oracle, emb_half, n, saved):
     rng = np.random.default_rng(35)
     emb = (rng.standard_normal((n, 32)) * 0.5).astype(np.float16 if emb_half else np.float32)
     dirs = rng.standard_normal((n, 3)).astype(np.float32)
@@ -371,7 +372,14 @@ def test_mlp_bwd_tcgen05_matches_oracle(ops, oracle, emb_half, n):
     dsig = (rng.standard_normal(n) * 0.1).astype(np.float32)
     drgb = (rng.standard_normal((n, 3)) * 0.1).astype(np.float16)
     demb_ref, gw_ref = oracle.mlp_bwd(emb, dirs, ws, dsig, drgb)
-    demb, gw = ops.mlp_bwd(T(emb), T(dirs), [T(w) for w in ws], T(dsig), T(drgb))
+    save = None
+    if saved:   # backward restarting from the activations the forward kept (h + fp16 rgb) instead of recomputing
+        sig_f, rgb_f, save = ops.mlp_fwd(T(emb), T(dirs), [T(w) for w in ws], with_save=True)
+        sig_n, rgb_n = ops.mlp_fwd(T(emb), T(dirs), [T(w) for w in ws])
+        assert torch.equal(sig_f, sig_n) and torch.equal(rgb_f, rgb_n)       # saving does not change the outputs
+        kept = save.view(torch.float16)
+        assert torch.equal(kept[n * 16:n * 16 + n * 4].view(n, 4)[:, :3], rgb_f)
+    demb, gw = ops.mlp_bwd(T(emb), T(dirs), [T(w) for w in ws], T(dsig), T(drgb), save=save)
     demb, gw = N(demb).astype(np.float32), N(gw)
     demb_ref = demb_ref.astype(np.float32)
     # every intermediate gradient is rounded to fp16 on both sides; the tensor core sums K in a
