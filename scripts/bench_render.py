@@ -46,3 +46,10 @@ torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / n
 print(f"impl={impl} ms/frame={dt * 1e3:.2f} fps={1 / dt:.1f} samples/ray={float(r['total_samples']) / 640000:.2f} "
       f"opacity_mean={float(r['opacity'].mean()):.4f} rgb_mean={float(r['rgb'].mean()):.4f}")
+if "--profile" in sys.argv:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            frame()
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=60))

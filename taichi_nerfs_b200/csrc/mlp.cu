@@ -532,10 +532,10 @@ __device__ __forceinline__ void epilogue_relu_bwd(uint32_t tmem_row, const uint8
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            // relu'(act) as a per-half bit mask (0xffff where act > 0): select semantics like threshold_backward,
+            // one HSET2.BM + LOP3 per pair instead of two unpack / compare / select chains
             const __half2 ah = *reinterpret_cast<const __half2*>(&aw[j]);
-            const float m0 = __low2float(ah) > 0.0f ? v[q * 8 + 2 * j] : 0.0f;
-            const float m1 = __high2float(ah) > 0.0f ? v[q * 8 + 2 * j + 1] : 0.0f;
-            o[j] = pack_h2(m0, m1);
+            o[j] = pack_h2(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]) & __hgt2_mask(ah, __float2half2_rn(0.0f));
         }
         *reinterpret_cast<uint4*>(dst + chunk_off(row, kc, 64)) = make_uint4(o[0], o[1], o[2], o[3]);
     }
