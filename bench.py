@@ -301,7 +301,8 @@ def run_ours(args):
                                    "beside ray_aabb + marching of step k+1 (flushed before every grid update and at "
                                    "the end of the timed region)")
                                 if fast is not None else "modules API: render() + torch.autograd + fused Adam"},
-        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "roofline": roof,
