@@ -510,3 +510,57 @@ def test_sample_ray_batch_matches_dataset_and_get_rays(oracle):
     # 'same_image' strategy (base.py:45-47)
     e = oracle.sample_ray_batch(bank, poses, dirs, 64, fixed_img=2, seed=1)
     assert (e["img_idxs"] == 2).all() and (e["rays_o"] == poses[2, :, 3]).all()
+
+
+def _closed_form_positions(t0, n, dt):
+    """t_{k+1} = fl32(t_k + dt) without the serial chain: inside one binade every step adds the same whole number
+    of ulps (dt = sqrt(3)/1024 has an odd mantissa, so the rounding never hits a tie for t >= NEAR_DISTANCE);
+    only the step that crosses into the next binade is taken with a real fp32 add."""
+    t = np.float32(t0)
+    out = [t]
+    while len(out) <= n:
+        bits = int(t.view(np.uint32))
+        e, m = (bits >> 23) & 0xFF, (bits & 0x7FFFFF) | 0x800000
+        t1 = np.float32(t + dt)
+        b1 = int(t1.view(np.uint32))
+        if (b1 >> 23) & 0xFF != e:
+            t = t1
+            out.append(t)
+            continue
+        c = ((b1 & 0x7FFFFF) | 0x800000) - m
+        j = min(n + 1 - len(out), (0xFFFFFF - m) // c)
+        if j == 0:
+            t = t1
+            out.append(t)
+            continue
+        ms = m + c * np.arange(1, j + 1, dtype=np.int64)
+        out.extend(((e << 23) | (ms & 0x7FFFFF)).astype(np.uint32).view(np.float32))
+        t = out[-1]
+    return np.array(out[: n + 1], np.float32)
+
+
+def test_constant_step_recurrence_has_closed_form(oracle, lego_bitfield, rays_factory):
+    """Property of the synthetic-scene march (exp_step_factor = 0, ray_march.py:45-74): every sample time of a ray lies
+    on ONE occupancy-independent fp32 sequence t_{k+1} = t_k + dt, and that sequence can be generated without the
+    serial add chain.  (Basis of the planned cell-stepping march)"""
+    dt = np.float32(1.7320508075688772 / 1024)
+    rng = np.random.default_rng(77)
+    for t0 in rng.uniform(0.01, 2.5, 200).astype(np.float32):
+        seq = [np.float32(t0)]
+        for _ in range(1100):
+            seq.append(np.float32(seq[-1] + dt))
+        assert np.array_equal(np.array(seq, np.float32).view(np.uint32),
+                              _closed_form_positions(t0, 1100, dt).view(np.uint32))
+    n = 257
+    o, d = rays_factory(n, seed=78)
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    noise = rng.random(n, dtype=np.float32)
+    ra, xyzs, dirs, deltas, ts, S = oracle.raymarching_train(o, d, hits, lego_bitfield, noise, 1, 0.5, 0.0, 128, 1024)
+    assert S > 1000
+    for r, s0, c in ra:
+        if c == 0:
+            continue
+        t0 = np.float32(hits[r, 0] + np.float32(dt * noise[r]))            # ray_march.py:36-38
+        grid = _closed_form_positions(t0, 1100, dt).view(np.uint32)
+        assert np.isin(ts[s0:s0 + c].view(np.uint32), grid).all()
+        assert (deltas[s0:s0 + c] == dt).all()
