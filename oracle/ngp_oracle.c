@@ -1001,3 +1001,106 @@ int ngp_sample_ray_batch_cpu(const float* image_bank, int channels, const float*
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Blueprint of the planned cell-stepping march (exp_step_factor == 0 only).              */
+/* Same loop as march_step / ray_march.py:45-74, except that the inner `while t < t_target: t += dt`     */
+/* is replaced by a closed-form jump: inside one fp32 binade every `t += dt` adds the same whole number  */
+/* of ulps, so the first candidate position >= t_target follows from one integer division; only a step   */
+/* that crosses into the next binade is taken with a real add.  Must emit bit-identical sample times     */
+/* (tests/test_oracle.py::test_cellstep_march_equals_reference_march).                                   */
+/* ------------------------------------------------------------------------- */
+static inline uint32_t f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
+static inline float u2f(uint32_t u) { float x; memcpy(&x, &u, 4); return x; }
+
+/* first position of the sequence t, t+dt, (t+dt)+dt, ... that is >= t_target, taking at least one step */
+static inline float advance_const_dt(float t, float dt, float t_target, int64_t* real_adds) {
+    float tn = t + dt;
+    *real_adds += 1;
+    while (tn < t_target) {
+        const uint32_t b = f2u(tn), e = b >> 23; /* tn > 0: no sign bit */
+        const float t1 = tn + dt;
+        const uint32_t b1 = f2u(t1);
+        *real_adds += 1;
+        if ((b1 >> 23) != e) { /* this step leaves the binade */
+            tn = t1;
+            continue;
+        }
+        const uint32_t m = (b & 0x7FFFFFu) | 0x800000u;
+        const uint32_t c = ((b1 & 0x7FFFFFu) | 0x800000u) - m; /* ulps per step in this binade */
+        const uint32_t kmax = (0xFFFFFFu - m) / c;              /* steps that stay inside it */
+        uint32_t k = kmax;
+        const uint32_t bt = f2u(t_target);
+        if ((bt >> 23) == e) { /* target in the same binade: a multiple of the same ulp */
+            const uint32_t need = ((bt & 0x7FFFFFu) | 0x800000u) - m;
+            const uint32_t kk = (need + c - 1) / c;
+            if (kk < k) k = kk;
+        }
+        if (k == 0) { /* next step crosses (cannot happen after the exponent check, kept for safety) */
+            tn = t1;
+            continue;
+        }
+        tn = u2f((e << 23) | ((m + k * c) & 0x7FFFFFu));
+    }
+    return tn;
+}
+
+int ngp_raymarching_cellstep_cpu(const float* rays_o, const float* rays_d, const float* hits_t,
+                                 const uint8_t* density_bitfield, const float* noise, int cascades,
+                                 int grid_size, float scale, int max_samples, const int32_t* rays_a,
+                                 float* ts, int32_t* counts, int64_t* stats /* [iterations, real adds] */,
+                                 int64_t n_rays) {
+    int64_t iters = 0, adds = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : iters, adds)
+    for (int64_t r = 0; r < n_rays; ++r) {
+        march_ctx c;
+        march_ctx_init(&c, rays_o + r * 3, rays_d + r * 3, cascades, grid_size, scale, 0.0f, density_bitfield);
+        const int gs = grid_size;
+        const float gsf = (float)gs, gs_inv = 1.0f / gsf;
+        const float t2 = hits_t[r * 2 + 1];
+        float t = march_train_t0(hits_t, noise, r, 0.0f, grid_size, scale);
+        const float dt = calc_dt(t, 0.0f, gs, scale); /* constant for exp_step_factor == 0 */
+        const int64_t start = rays_a[r * 3 + 1];
+        int n = 0;
+        uint32_t last_idx = 0xFFFFFFFFu;
+        int last_occ = 0;
+        while (0.0f <= t && t < t2 && n < max_samples) {
+            iters += 1;
+            float xyz[3], nxyz[3];
+            uint32_t u[3];
+            for (int k = 0; k < 3; ++k) xyz[k] = c.o[k] + t * c.d[k];
+            const int mip = imax(mip_from_pos(xyz[0], xyz[1], xyz[2], cascades), mip_from_dt(dt, gs, cascades));
+            const float mip_bound = fminf(ldexpf(1.0f, mip - 1), scale);
+            const float mip_bound_inv = 1.0f / mip_bound;
+            for (int k = 0; k < 3; ++k) {
+                float v = 0.5f * (xyz[k] * mip_bound_inv + 1.0f) * gsf;
+                v = fminf(fmaxf(v, 0.0f), gsf - 1.0f);
+                nxyz[k] = v;
+                u[k] = (uint32_t)v;
+            }
+            const uint32_t idx = (uint32_t)mip * (uint32_t)(gs * gs * gs) + morton3d(u[0], u[1], u[2]);
+            if (idx != last_idx) { /* consecutive positions in one cell share the bitfield lookup */
+                last_idx = idx;
+                last_occ = (density_bitfield[idx >> 3] >> (idx & 7u)) & 1;
+            }
+            if (last_occ) {
+                ts[start + n] = t;
+                n += 1;
+                t += dt;
+                adds += 1;
+                continue;
+            }
+            float tmin = INFINITY;
+            for (int k = 0; k < 3; ++k) {
+                const float tx =
+                    (((nxyz[k] + 0.5f + 0.5f * fsign(c.d[k])) * gs_inv * 2.0f - 1.0f) * mip_bound - xyz[k]) * c.dinv[k];
+                tmin = fminf(tmin, tx);
+            }
+            t = advance_const_dt(t, dt, t + fmaxf(0.0f, tmin), &adds);
+        }
+        counts[r] = n;
+    }
+    stats[0] = iters;
+    stats[1] = adds;
+    return 0;
+}

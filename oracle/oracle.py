@@ -323,3 +323,18 @@ def sample_ray_batch(image_bank, poses, directions, n_rays, img_idxs=None, pix_i
                                         C.c_int64(fixed_img), C.c_uint64(seed), C.c_int32(step), _p(o), _p(d), n(rgb),
                                         _p(noise), _p(io), _p(po), C.c_int64(n_rays)))
     return {"rays_o": o, "rays_d": d, "rgb": rgb, "noise": noise, "img_idxs": io, "pix_idxs": po}
+
+
+def raymarching_cellstep(rays_o, rays_d, hits_t, bitfield, noise, cascades, scale, grid_size, max_samples, rays_a,
+                         n_samples):
+    """Cell-stepping blueprint (exp_step_factor == 0): sample times in the layout of ``rays_a`` + loop statistics."""
+    o, d, h = _c(rays_o, np.float32), _c(rays_d, np.float32), _c(hits_t, np.float32)
+    bf, nz, ra = _c(bitfield, np.uint8), _c(noise, np.float32), _c(rays_a, np.int32)
+    n = o.shape[0]
+    ts = np.zeros(n_samples, np.float32)
+    counts = np.zeros(n, np.int32)
+    stats = np.zeros(2, np.int64)
+    _chk(lib().ngp_raymarching_cellstep_cpu(_p(o), _p(d), _p(h), _p(bf), _p(nz), C.c_int(cascades), C.c_int(grid_size),
+                                            C.c_float(scale), C.c_int(max_samples), _p(ra), _p(ts), _p(counts),
+                                            _p(stats), C.c_int64(n)))
+    return ts, counts, {"iterations": int(stats[0]), "real_adds": int(stats[1])}

@@ -564,3 +564,58 @@ def test_constant_step_recurrence_has_closed_form(oracle, lego_bitfield, rays_fa
         grid = _closed_form_positions(t0, 1100, dt).view(np.uint32)
         assert np.isin(ts[s0:s0 + c].view(np.uint32), grid).all()
         assert (deltas[s0:s0 + c] == dt).all()
+
+
+@pytest.mark.parametrize("occ", ["lego", "random", "full"])
+def test_cellstep_march_equals_reference_march(oracle, lego_bitfield, rays_factory, occ):
+    """The cell-stepping loop (closed-form jump over empty cells, one bitfield lookup per cell) emits exactly the
+    sample times of the reference-shaped loop — the blueprint for the next marching kernel."""
+    rng = np.random.default_rng(90)
+    n = 1500
+    o, d = rays_factory(n, seed=90)
+    d[:40] *= -1                                  # rays pointing away / grazing
+    bits = {"lego": lego_bitfield, "random": rng.integers(0, 256, 128 ** 3 // 8, dtype=np.uint8),
+            "full": np.full(128 ** 3 // 8, 255, np.uint8)}[occ]
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    noise = rng.random(n, dtype=np.float32)
+    for max_samples in (1024, 37):
+        ra, xyzs, dirs, deltas, ts, S = oracle.raymarching_train(o, d, hits, bits, noise, 1, 0.5, 0.0, 128, max_samples)
+        ts2, counts, st = oracle.raymarching_cellstep(o, d, hits, bits, noise, 1, 0.5, 128, max_samples, ra, S)
+        assert np.array_equal(counts, ra[:, 2])
+        assert np.array_equal(ts2.view(np.uint32), ts.view(np.uint32))
+    # loop statistics: the inner `while t < t_target` chain is gone (about one real fp32 add per iteration)
+    assert st["real_adds"] < 1.1 * st["iterations"] + n
+
+
+def test_reference_exit_quirk_visits_every_candidate_position(oracle, rays_factory):
+    """ray_march.py:66-71 computes the cell exit from the UN-floored grid coordinate, so along an axis with d < 0
+    the "exit" is the sample position itself: t_target == t and the loop advances by exactly one step.  Hence, for a
+    ray with a negative direction component, the emitted samples are exactly the occupied positions of the
+    occupancy-independent t sequence — except inside the outermost half cell, where the coordinate is clamped to
+    grid_size - 1 and a real multi-step jump happens.  (Why empty-space skipping buys the reference nothing, and
+    the basis of the independent-positions marching fast path planned in DESIGN.md §7.)"""
+    f32 = np.float32
+    rng = np.random.default_rng(3)
+    n = 1200
+    o, d = rays_factory(n, seed=11)
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    noise = rng.random(n, dtype=np.float32)
+    bits = rng.integers(0, 256, 128 ** 3 // 8, dtype=np.uint8)
+    full = np.full(128 ** 3 // 8, 255, np.uint8)
+    ra_f, x_f, _, _, ts_f, _ = oracle.raymarching_train(o, d, hits, full, noise, 1, 0.5, 0.0, 128, 4096)   # every position
+    ra, _, _, _, ts, _ = oracle.raymarching_train(o, d, hits, bits, noise, 1, 0.5, 0.0, 128, 4096)
+    v = (f32(0.5) * (x_f * f32(2.0) + f32(1.0))).astype(np.float32) * f32(128.0)       # utils/ray_march grid coordinate
+    v = np.minimum(np.maximum(v, f32(0)), f32(127)).astype(np.float32)
+    idx = oracle.morton3d(v.astype(np.int32)).astype(np.int64)
+    occ = ((bits[idx >> 3] >> (idx & 7)) & 1).astype(bool)
+    checked = 0
+    for r in range(n):
+        if d[r].min() > -1e-3:
+            continue
+        s0, c = ra_f[r, 1], ra_f[r, 2]
+        emitted = np.isin(ts_f[s0:s0 + c].view(np.uint32), ts[ra[r, 1]:ra[r, 1] + ra[r, 2]].view(np.uint32))
+        differ = emitted != occ[s0:s0 + c]
+        assert not emitted[~occ[s0:s0 + c]].any()                               # nothing is emitted from an empty cell
+        assert (v[s0:s0 + c][differ] == 127.0).any(axis=1).all()                # skipped positions: clamped layer only
+        checked += 1
+    assert checked > n // 2
