@@ -1104,3 +1104,80 @@ int ngp_raymarching_cellstep_cpu(const float* rays_o, const float* rays_d, const
     stats[1] = adds;
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Lane-level emulation of the planned warp-per-ray marching fast path: 32 candidate       */
+/* positions per chunk, lane k holds position k.  A chunk is REGULAR when every in-box lane is either      */
+/* occupied or has an axis with d < -1e-3 whose grid coordinate is not clamped — then each visited          */
+/* position's successor is the next position (exit quirk, see the tests) and emit = occupied lanes; any     */
+/* other chunk, and any chunk entered with a pending jump, goes through the sequential reference loop.      */
+/* Returns sample times in the layout of rays_a and the number of regular / general chunks.                 */
+/* ------------------------------------------------------------------------- */
+int ngp_raymarching_lanes_cpu(const float* rays_o, const float* rays_d, const float* hits_t,
+                              const uint8_t* density_bitfield, const float* noise, int grid_size, float scale,
+                              int max_samples, const int32_t* rays_a, float* ts, int32_t* counts,
+                              int64_t* stats /* [regular chunks, general chunks] */, int64_t n_rays) {
+    int64_t n_reg = 0, n_gen = 0;
+    const int gs = grid_size;
+    const float gsf = (float)gs;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : n_reg, n_gen)
+    for (int64_t r = 0; r < n_rays; ++r) {
+        march_ctx c;
+        march_ctx_init(&c, rays_o + r * 3, rays_d + r * 3, 1, grid_size, scale, 0.0f, density_bitfield);
+        const float t2 = hits_t[r * 2 + 1];
+        float t = march_train_t0(hits_t, noise, r, 0.0f, grid_size, scale);
+        const float dt = calc_dt(t, 0.0f, gs, scale);
+        const float mip_bound = fminf(0.5f, scale), mip_bound_inv = 1.0f / mip_bound;
+        const int64_t start = rays_a[r * 3 + 1];
+        int n = 0;
+        while (0.0f <= t && t < t2 && n < max_samples) {
+            /* candidate positions of this chunk (the occupancy-independent sequence) */
+            float pos[33];
+            pos[0] = t;
+            for (int k = 1; k <= 32; ++k) pos[k] = pos[k - 1] + dt;
+            int regular = 1, occ[32], valid[32];
+            for (int k = 0; k < 32; ++k) {
+                valid[k] = pos[k] < t2;
+                occ[k] = 0;
+                if (!valid[k]) continue;
+                int ok = 0;
+                uint32_t u[3];
+                for (int a = 0; a < 3; ++a) {
+                    const float x = c.o[a] + pos[k] * c.d[a];
+                    const float raw = 0.5f * (x * mip_bound_inv + 1.0f) * gsf;
+                    if (c.d[a] < -1e-3f && raw < gsf - 1.0f) ok = 1; /* exit distance ~0 along this axis */
+                    u[a] = (uint32_t)fminf(fmaxf(raw, 0.0f), gsf - 1.0f);
+                }
+                const uint32_t idx = morton3d(u[0], u[1], u[2]);
+                occ[k] = (density_bitfield[idx >> 3] >> (idx & 7u)) & 1;
+                if (!occ[k] && !ok) regular = 0;
+            }
+            if (regular) {
+                n_reg += 1;
+                int k = 0;
+                for (; k < 32 && valid[k] && n < max_samples; ++k)
+                    if (occ[k]) ts[start + n++] = pos[k];
+                if (k < 32) break; /* left the box or hit the sample cap inside this chunk */
+                t = pos[32];
+            } else {
+                /* general path: the reference loop over this chunk's span (may overshoot into the next span) */
+                n_gen += 1;
+                const float t_end = pos[32];
+                float xyz[3], dts;
+                while (0.0f <= t && t < t2 && n < max_samples && t < t_end) {
+                    float tt = t;
+                    if (march_step(&c, &tt, xyz, &dts)) {
+                        ts[start + n++] = t;
+                        t += dts;
+                    } else {
+                        t = tt;
+                    }
+                }
+            }
+        }
+        counts[r] = n;
+    }
+    stats[0] = n_reg;
+    stats[1] = n_gen;
+    return 0;
+}

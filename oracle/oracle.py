@@ -338,3 +338,16 @@ def raymarching_cellstep(rays_o, rays_d, hits_t, bitfield, noise, cascades, scal
                                             C.c_float(scale), C.c_int(max_samples), _p(ra), _p(ts), _p(counts),
                                             _p(stats), C.c_int64(n)))
     return ts, counts, {"iterations": int(stats[0]), "real_adds": int(stats[1])}
+
+
+def raymarching_lanes(rays_o, rays_d, hits_t, bitfield, noise, scale, grid_size, max_samples, rays_a, n_samples):
+    """Lane-level emulation of the planned marching fast path (cascades == 1, exp_step_factor == 0)."""
+    o, d, h = _c(rays_o, np.float32), _c(rays_d, np.float32), _c(hits_t, np.float32)
+    bf, nz, ra = _c(bitfield, np.uint8), _c(noise, np.float32), _c(rays_a, np.int32)
+    n = o.shape[0]
+    ts = np.zeros(n_samples, np.float32)
+    counts = np.zeros(n, np.int32)
+    stats = np.zeros(2, np.int64)
+    _chk(lib().ngp_raymarching_lanes_cpu(_p(o), _p(d), _p(h), _p(bf), _p(nz), C.c_int(grid_size), C.c_float(scale),
+                                         C.c_int(max_samples), _p(ra), _p(ts), _p(counts), _p(stats), C.c_int64(n)))
+    return ts, counts, {"regular_chunks": int(stats[0]), "general_chunks": int(stats[1])}

@@ -619,3 +619,23 @@ def test_reference_exit_quirk_visits_every_candidate_position(oracle, rays_facto
         assert (v[s0:s0 + c][differ] == 127.0).any(axis=1).all()                # skipped positions: clamped layer only
         checked += 1
     assert checked > n // 2
+
+
+def test_chunked_fast_path_emulation_equals_reference_march(oracle, lego_bitfield, rays_factory):
+    """Lane-level emulation of the planned warp kernel: chunks whose empty lanes all have a negative, unclamped axis
+    take the independent-positions path (emit = occupied lanes), the rest the sequential loop — same sample times,
+    and the fast path covers the bulk of the chunks."""
+    rng = np.random.default_rng(91)
+    n = 2500
+    o, d = rays_factory(n, seed=91)
+    d[:200] = np.abs(d[:200])                     # all-positive directions: the only rays with real jumps
+    d[200:240, 2] = 0.0                           # axis-parallel components (1/d = inf)
+    hits = oracle.ray_aabb_intersect(o, d, 0.5)
+    noise = rng.random(n, dtype=np.float32)
+    for bits in (lego_bitfield, rng.integers(0, 256, 128 ** 3 // 8, dtype=np.uint8)):
+        for max_samples in (1024, 50):
+            ra, _, _, _, ts, S = oracle.raymarching_train(o, d, hits, bits, noise, 1, 0.5, 0.0, 128, max_samples)
+            ts2, counts, st = oracle.raymarching_lanes(o, d, hits, bits, noise, 0.5, 128, max_samples, ra, S)
+            assert np.array_equal(counts, ra[:, 2])
+            assert np.array_equal(ts2.view(np.uint32), ts.view(np.uint32))
+            assert st["regular_chunks"] > 8 * st["general_chunks"]
