@@ -1134,7 +1134,19 @@ int ngp_raymarching_lanes_cpu(const float* rays_o, const float* rays_d, const fl
             /* candidate positions of this chunk (the occupancy-independent sequence) */
             float pos[33];
             pos[0] = t;
-            for (int k = 1; k <= 32; ++k) pos[k] = pos[k - 1] + dt;
+            {
+                /* lane k's position without the serial chain when the 33 positions share t's binade: k steps add
+                 * k * c ulps (c = ulps per step in this binade); otherwise (a binade boundary inside the chunk,
+                 * once or twice per ray) fall back to the sequential adds */
+                const uint32_t b = f2u(t), e = b >> 23, m = (b & 0x7FFFFFu) | 0x800000u;
+                const uint32_t b1 = f2u(t + dt);
+                const uint32_t cstep = ((b1 & 0x7FFFFFu) | 0x800000u) - m;
+                if ((b1 >> 23) == e && (uint64_t)m + 32ull * cstep <= 0xFFFFFFull) {
+                    for (int k = 1; k <= 32; ++k) pos[k] = u2f((e << 23) | ((m + (uint32_t)k * cstep) & 0x7FFFFFu));
+                } else {
+                    for (int k = 1; k <= 32; ++k) pos[k] = pos[k - 1] + dt;
+                }
+            }
             int regular = 1, occ[32], valid[32];
             for (int k = 0; k < 32; ++k) {
                 valid[k] = pos[k] < t2;
