@@ -263,10 +263,21 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
         // t chain: position k of this chunk, identical on every lane
         float tk = t, my_t = t, my_dt = dt0;
         if (const_dt) {
+            // inside one binade every `t += dt` adds the same whole number of ulps (tests/test_oracle.py, closed form):
+            // lane k's position is k steps away without the serial chain; a chunk that contains a binade boundary
+            // (once or twice per ray) falls back to the sequential adds
+            const uint32_t b = __float_as_uint(t), e = b >> 23, m = (b & 0x7fffffu) | 0x800000u;
+            const uint32_t b1 = __float_as_uint(f_add(t, dt0));
+            const uint32_t cs = ((b1 & 0x7fffffu) | 0x800000u) - m;
+            if ((b1 >> 23) == e && m + 32u * cs <= 0xffffffu) {
+                my_t = __uint_as_float((e << 23) | ((m + (uint32_t)lane * cs) & 0x7fffffu));
+                tk = __uint_as_float((e << 23) | ((m + 32u * cs) & 0x7fffffu));
+            } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if (k == lane) my_t = tk;
-                tk = f_add(tk, dt0);
+                for (int k = 0; k < 32; ++k) {
+                    if (k == lane) my_t = tk;
+                    tk = f_add(tk, dt0);
+                }
             }
         } else {
 #pragma unroll 8
