@@ -159,9 +159,12 @@ __global__ void __launch_bounds__(256) ray_aabb_kernel(const float* __restrict__
 // short shuffle pointer walk.  Samples come out in the same order with the same bits.
 struct CellTest {
     float xyz[3];
+    float nxyz[3];   // clamped grid coordinate (kept un-floored: the reference's exit uses it as is)
+    float mip_bound;
     float dt;
-    float t_target;  // exit time of the (empty) cell, ray_march.py:66-71
     bool occ;
+    bool regular;    // some axis has d < -1e-3 with an unclamped coordinate: the exit distance along it is ~0, so
+                     // the reference loop advances by exactly ONE step from here (tests/test_oracle.py, exit quirk)
 };
 
 __device__ __forceinline__ CellTest test_cell(const MarchParams& p, const Ray& ray, float tt, float dt) {
@@ -178,27 +181,33 @@ __device__ __forceinline__ CellTest test_cell(const MarchParams& p, const Ray& r
     }
     const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + mip - 1) << 23), p.scale);
     const float mip_bound_inv = f_div(1.0f, mip_bound);
-    float nxyz[3];
     uint32_t u[3];
+    c.regular = false;
+    c.mip_bound = mip_bound;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float v = f_mul(f_mul(0.5f, f_add(f_mul(c.xyz[k], mip_bound_inv), 1.0f)), p.gsf);
-        v = fminf(fmaxf(v, 0.0f), f_sub(p.gsf, 1.0f));
-        nxyz[k] = v;
+        const float raw = f_mul(f_mul(0.5f, f_add(f_mul(c.xyz[k], mip_bound_inv), 1.0f)), p.gsf);
+        c.regular = c.regular || (ray.d[k] < -1e-3f && raw < f_sub(p.gsf, 1.0f));
+        const float v = fminf(fmaxf(raw, 0.0f), f_sub(p.gsf, 1.0f));
+        c.nxyz[k] = v;
         u[k] = __float2uint_rz(v);
     }
     const uint32_t idx = (uint32_t)mip * p.gs3 + morton3d(u[0], u[1], u[2]);
     c.occ = ((uint32_t)__ldg(p.bits + (idx >> 3)) & (1u << (idx & 7u))) != 0;
+    return c;
+}
+
+// exit time of the (empty) cell, ray_march.py:66-71
+__device__ __forceinline__ float cell_exit(const MarchParams& p, const Ray& ray, const CellTest& c, float tt) {
     float tmin = INFINITY;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float a = f_add(f_add(nxyz[k], 0.5f), f_mul(0.5f, fsign(ray.d[k])));
+        float a = f_add(f_add(c.nxyz[k], 0.5f), f_mul(0.5f, fsign(ray.d[k])));
         a = f_sub(f_mul(f_mul(a, p.gs_inv), 2.0f), 1.0f);
-        a = f_mul(f_sub(f_mul(a, mip_bound), c.xyz[k]), ray.dinv[k]);
+        a = f_mul(f_sub(f_mul(a, c.mip_bound), c.xyz[k]), ray.dinv[k]);
         tmin = fminf(tmin, a);
     }
-    c.t_target = f_add(tt, fmaxf(0.0f, tmin));
-    return c;
+    return f_add(tt, fmaxf(0.0f, tmin));
 }
 
 constexpr int kRaysPerBlock = 4;
@@ -254,10 +263,21 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
         // t chain: position k of this chunk, identical on every lane
         float tk = t, my_t = t, my_dt = dt0;
         if (const_dt) {
+            // inside one binade every `t += dt` adds the same whole number of ulps (tests/test_oracle.py, closed form):
+            // lane k's position is k steps away without the serial chain; a chunk that contains a binade boundary
+            // (once or twice per ray) falls back to the sequential adds
+            const uint32_t b = __float_as_uint(t), e = b >> 23, m = (b & 0x7fffffu) | 0x800000u;
+            const uint32_t b1 = __float_as_uint(f_add(t, dt0));
+            const uint32_t cs = ((b1 & 0x7fffffu) | 0x800000u) - m;
+            if ((b1 >> 23) == e && m + 32u * cs <= 0xffffffu) {
+                my_t = __uint_as_float((e << 23) | ((m + (uint32_t)lane * cs) & 0x7fffffu));
+                tk = __uint_as_float((e << 23) | ((m + 32u * cs) & 0x7fffffu));
+            } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if (k == lane) my_t = tk;
-                tk = f_add(tk, dt0);
+                for (int k = 0; k < 32; ++k) {
+                    if (k == lane) my_t = tk;
+                    tk = f_add(tk, dt0);
+                }
             }
         } else {
 #pragma unroll 8
@@ -275,6 +295,18 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
         const unsigned valid_mask = __ballot_sync(full, valid);
         const unsigned occ_mask = __ballot_sync(full, valid && c.occ);
 
+        // Independent-positions fast path: if every in-box lane is occupied or "regular" (and no jump is pending from
+        // the previous chunk) each visited position's successor is simply the next one, so the visited set is the
+        // whole chunk and the emitted samples are its occupied lanes — no exit times, search or pointer walk.
+        const bool chunk_regular = const_dt && p.cascades == 1 && skip_until == -INFINITY &&
+                                   __all_sync(full, !valid || c.occ || c.regular);
+        unsigned emit = 0;
+        if (chunk_regular) {
+            emit = occ_mask;
+            const int room = limit - emitted;
+            if (__popc(emit) > room) emit &= (1u << __fns(emit, 0, room + 1)) - 1u;  // max_samples cap
+        } else {
+        const float t_target = cell_exit(p, ray, c, my_t);
         // empty lanes: first position j > lane with t_j >= t_target (at least one step, ray_march.py:72-74)
         int lo = lane + 1, hi = 32;
 #pragma unroll
@@ -282,7 +314,7 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
             const int mid = (lo + hi) >> 1;
             const float tm = __shfl_sync(full, my_t, min(mid, 31));
             if (lo < hi) {
-                if (tm < c.t_target) lo = mid + 1;
+                if (tm < t_target) lo = mid + 1;
                 else hi = mid;
             }
         }
@@ -305,7 +337,6 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
         }
         // entry position: skip the positions still inside the cell left at the end of the previous chunk
         const int pos0 = __popc(__ballot_sync(full, my_t < skip_until));
-        unsigned emit = 0;
         if (pos0 < 32) {
             const unsigned visited = __shfl_sync(full, M, pos0) & valid_mask;
             emit = visited & occ_mask;
@@ -315,9 +346,10 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
             if (visited) {
                 const int q = 31 - __clz(visited);  // last visited position
                 const int nq = __shfl_sync(full, nxt, q);
-                const float tq = __shfl_sync(full, c.t_target, q);
+                const float tq = __shfl_sync(full, t_target, q);
                 if (!((occ_mask >> q) & 1u) && nq >= 32) skip_until = tq;  // cell extends into the next chunk
             }
+        }
         }
         if (kWrite && ((emit >> lane) & 1u)) {
             const int64_t i = start + emitted + __popc(emit & ((1u << lane) - 1u));
