@@ -206,6 +206,11 @@ int ngp_dir_encode(const float* dirs, float* out, int64_t n, void* stream);
  * forms sigmoid' from the saved output exactly as torch's sigmoid_backward does.  save == NULL: the backward
  * recomputes everything from (emb, dirs). */
 int64_t ngp_mlp_save_bytes(int64_t n);
+/* Selects the forward implementation for fp16 embeddings: 0 = auto (v2 where it applies), 1 = v1 (activations
+ * in shared memory, mlp.cu), 2 = v2 (TMA-fed, activations in tensor memory, mlp_fwd_v2.cu; an error instead of a
+ * silent fall-back when it cannot run).  Same results bit for bit; exists for A/B timing and the parity tests.
+ * The environment variable NGP_MLP_FWD overrides the argument. */
+int ngp_mlp_set_impl(int fwd_impl);
 int ngp_mlp_fwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w,
                 float* sigmas, void* rgbs_f16, void* save, int64_t n, void* stream);
 /* backward: dsigmas [n] fp32, drgbs [n,3] fp16 -> demb [n,32] (emb dtype) and

@@ -34,8 +34,22 @@ def t(fn, reps=7):
     return statistics.median(out)
 
 
-for name, fn in [("fwd", lambda: ops.mlp_fwd(emb, dirs, ws)), ("fwd+save", lambda: ops.mlp_fwd(emb, dirs, ws, with_save=True)),
+from taichi_nerfs_b200 import _lib
+
+for impl, tag in ((1, "v1 smem"), (2, "v2 tmem")):
+    _lib.load().ngp_mlp_set_impl(impl)
+    for name, fn in [("fwd", lambda: ops.mlp_fwd(emb, dirs, ws)), ("fwd+save", lambda: ops.mlp_fwd(emb, dirs, ws, with_save=True))]:
+        try:
+            fn()
+            us = t(fn) * 1e3
+            print(f"{name + ' ' + tag:22s} {us:8.1f} us   (n = {n}; {18816 * n / us / 1e6:6.1f} TFLOP/s, "
+                  f"{(86 + (40 if 'save' in name else 0)) * n / us / 1e3:6.0f} GB/s algorithmic)", flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"{name} {tag}: FAILED {e}", flush=True)
+_lib.load().ngp_mlp_set_impl(0)
+for name, fn in [
                  ("bwd recompute", lambda: ops.mlp_bwd(emb, dirs, ws, dsig, drgb)),
                  ("bwd saved", lambda: ops.mlp_bwd(emb, dirs, ws, dsig, drgb, save=save))]:
     fn()
-    print(f"{name:14s} {t(fn) * 1e3:8.1f} us   (n = {n})")
+    us = t(fn) * 1e3
+    print(f"{name:22s} {us:8.1f} us   (n = {n}; {37632 * n / us / 1e6:6.1f} TFLOP/s)", flush=True)

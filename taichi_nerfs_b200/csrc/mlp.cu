@@ -19,11 +19,18 @@
 // Roofline: tensor pipe for the MMAs (18,816 FLOP/sample forward) but K is only 32/64, so the
 // kernel is bounded by the TMEM->register->shared epilogue round trips and by 86 B/sample of HBM
 // traffic (emb 64 B + dir 12 B in, sigma 4 B + rgb 6 B out); see DESIGN.md.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "tcgen05.cuh"
+
+namespace ngp {
+int mlp_fwd_v2_launch(const void* emb_f16, const float* dirs, const ngp_mlp_weights* w, float* sigmas, void* rgbs,
+                      void* save, int64_t n, const int32_t* n_dev, cudaStream_t st);
+}
 
 namespace {
+using namespace ngp_tc;
 
-constexpr int kTile = 128;          // samples per tile == UMMA M
 constexpr int kRows = 128;          // sample rows per tile == TMEM lanes
 constexpr int kThreads = 256;       // TWO threads per row: warps 0-3 own accumulator columns [0,32), warps 4-7 own [32,64)
 constexpr int kThreadsBwd = 288;    // backward: + warp 8, which only issues MMAs (the 8-MMA weight-gradient batches of a
@@ -31,13 +38,7 @@ constexpr int kThreadsBwd = 288;    // backward: + warp 8, which only issues MMA
                                     // (a warp may touch TMEM lanes 32*(warp%4)..+31), halving every epilogue's latency
 constexpr uint32_t kTmemCols = 64;  // fp32 accumulator columns (max N = 64)
 
-// shared memory map (bytes).  Weights first (shared by both kernels), then activation buffers.
-constexpr int kW1 = 0;                       // [64 x 32]
-constexpr int kW2 = kW1 + 64 * 32 * 2;       // [16 x 64]
-constexpr int kW3 = kW2 + 16 * 64 * 2;       // [64 x 32]
-constexpr int kW4 = kW3 + 64 * 32 * 2;       // [64 x 64]
-constexpr int kW5 = kW4 + 64 * 64 * 2;       // [16 x 64] (rows 3..15 zero)
-constexpr int kAct = kW5 + 16 * 64 * 2;      // 20480
+// shared memory map (bytes).  Weights first (tcgen05.cuh, shared by all MLP kernels), then activation buffers.
 constexpr int kB64 = kTile * 64 * 2;         // one [128 x 64] fp16 operand buffer
 constexpr int kB32 = kTile * 32 * 2;
 constexpr int kB16 = kTile * 16 * 2;
@@ -72,168 +73,6 @@ __device__ long long g_mlp_trace[2 * 4 * 32];
 #else
 #define NGP_TR(k) ((void)0)
 #endif
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {  // whole warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16, issued by ONE thread
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread i of warp w = lane 32w+i)
-// issue only; the registers are valid after tmem_ld_wait()
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t r[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
-    uint32_t r[16];
-    tmem_ld16_issue(taddr, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// 32 accumulator columns (two pipelined loads, one wait)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
-    uint32_t r[32];
-    tmem_ld16_issue(taddr, r);
-    tmem_ld16_issue(taddr + 16, r + 16);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-// ---- descriptors -------------------------------------------------------------------------------------
-// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N
-__host__ __device__ constexpr uint32_t idesc_f16(int m, int n) {
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-// byte offset of the 16-byte chunk (row r, k-chunk kc) inside an operand with K columns
-__device__ __forceinline__ int chunk_off(int r, int kc, int K) { return (r >> 3) * (K * 16) + kc * 128 + (r & 7) * 16; }
-
-// one GEMM layer: D[128 x N] = A[128 x K] * W[N x K]^T   (K in {16,32,64})
-__device__ __forceinline__ void issue_layer_mma(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int K, int N) {
-    const uint32_t idesc = idesc_f16(kTile, N);
-    const uint32_t sbo = (uint32_t)K * 16;  // (K/8)*128
-    for (int k = 0; k < K / 16; ++k) {
-        const uint64_t da = smem_desc(a_addr + k * 256, 128, sbo);
-        const uint64_t db = smem_desc(w_addr + k * 256, 128, sbo);
-        umma_f16(tmem_d, da, db, idesc, k > 0 ? 1u : 0u);
-    }
-}
-__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int K, int N,
-                                            uint32_t bar) {
-    issue_layer_mma(tmem_d, a_addr, w_addr, K, N);
-    umma_commit(bar);
-}
-
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-// relu fused into the conversion (one F2FP instead of two FMNMX + F2FP); low half = a
-__device__ __forceinline__ uint32_t pack_h2_relu(float a, float b) {
-    uint32_t r;
-    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-    return r;
-}
-
-// copy a row-major fp32 weight [rows x K] into the interleaved fp16 operand layout (rows_pad rows)
-__device__ __forceinline__ void stage_weight(uint8_t* smem, const float* __restrict__ w, int rows, int rows_pad, int K) {
-    const int kchunks = K / 8;
-    if (threadIdx.x >= kThreads) return;  // the backward's MMA-issue warp does not stage
-    for (int c = threadIdx.x; c < rows_pad * kchunks; c += kThreads) {
-        const int r = c / kchunks, kc = c % kchunks;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (r < rows) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(w + r * K + kc * 8));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(w + r * K + kc * 8 + 4));
-            v = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
-        }
-        *reinterpret_cast<uint4*>(smem + chunk_off(r, kc, K)) = v;
-    }
-}
-
-__device__ __forceinline__ void sh16(float x, float y, float z, float* e) {  // spherical_harmonics.py:16-42
-    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
-    e[0] = 0.28209479177387814f;
-    e[1] = -0.48860251190291987f * y;
-    e[2] = 0.48860251190291987f * z;
-    e[3] = -0.48860251190291987f * x;
-    e[4] = 1.0925484305920792f * xy;
-    e[5] = -1.0925484305920792f * yz;
-    e[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-    e[7] = -1.0925484305920792f * xz;
-    e[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-    e[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
-    e[10] = 2.8906114426405538f * xy * z;
-    e[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
-    e[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
-    e[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
-    e[14] = 1.4453057213202769f * z * (x2 - y2);
-    e[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
-}
-
-// hidden-layer epilogue: TMEM [128 x 64] fp32 -> relu -> fp16 -> next operand buffer (K = 64 layout);
-// thread (row, hh) converts columns [32*hh, 32*hh+32) = chunks 4*hh .. 4*hh+3
-__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, uint8_t* dst, int row, int hh) {
-    float v[32];
-    tmem_ld32(tmem_row + hh * 32, v);
-#pragma unroll
-    for (int kc = 0; kc < 4; ++kc) {
-        const float* q = v + kc * 8;
-        *reinterpret_cast<uint4*>(dst + chunk_off(row, hh * 4 + kc, 64)) =
-            make_uint4(pack_h2_relu(q[0], q[1]), pack_h2_relu(q[2], q[3]), pack_h2_relu(q[4], q[5]),
-                       pack_h2_relu(q[6], q[7]));
-    }
-}
 
 // per-thread inputs of one tile row, fetched one tile ahead so the ~1 us DRAM latency overlaps the
 // previous tile's MMA / epilogue rounds
@@ -301,11 +140,11 @@ __global__ void __launch_bounds__(kThreads, 4) mlp_fwd_kernel(const TEmb* __rest
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBar + 8);
 
     // ---- one-time setup: weights -> smem, mbarrier, TMEM allocation
-    stage_weight(smem + kW1, w.w1, 64, 64, 32);
-    stage_weight(smem + kW2, w.w2, 16, 16, 64);
-    stage_weight(smem + kW3, w.w3, 64, 64, 32);
-    stage_weight(smem + kW4, w.w4, 64, 64, 64);
-    stage_weight(smem + kW5, w.w5, 3, 16, 64);
+    stage_weight(smem + kW1, w.w1, 64, 64, 32, kThreads);
+    stage_weight(smem + kW2, w.w2, 16, 16, 64, kThreads);
+    stage_weight(smem + kW3, w.w3, 64, 64, 32, kThreads);
+    stage_weight(smem + kW4, w.w4, 64, 64, 64, kThreads);
+    stage_weight(smem + kW5, w.w5, 3, 16, 64, kThreads);
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_barrier_init();
@@ -557,11 +396,11 @@ __global__ void __launch_bounds__(kThreadsBwd, 2) mlp_bwd_kernel(const TEmb* __r
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kBarBwd + 8);
     uint32_t phase2 = 0;
 
-    stage_weight(smem + kW1, w.w1, 64, 64, 32);
-    stage_weight(smem + kW2, w.w2, 16, 16, 64);
-    stage_weight(smem + kW3, w.w3, 64, 64, 32);
-    stage_weight(smem + kW4, w.w4, 64, 64, 64);
-    stage_weight(smem + kW5, w.w5, 3, 16, 64);
+    stage_weight(smem + kW1, w.w1, 64, 64, 32, kThreads);
+    stage_weight(smem + kW2, w.w2, 16, 16, 64, kThreads);
+    stage_weight(smem + kW3, w.w3, 64, 64, 32, kThreads);
+    stage_weight(smem + kW4, w.w4, 64, 64, 64, kThreads);
+    stage_weight(smem + kW5, w.w5, 3, 16, 64, kThreads);
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_init(bar2, 1);
@@ -824,9 +663,17 @@ int launch_bwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, con
     return 0;
 }
 
+// forward implementation: 0 = auto (v2 where it applies), 1 = v1 (shared-memory activations), 2 = v2 (TMEM activations)
+int g_fwd_impl = 0;
+
 template <typename TEmb>
 int launch_fwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, float* sigmas, void* rgbs, void* save,
                int64_t n, const int32_t* n_dev, cudaStream_t st) {
+    if (sizeof(TEmb) == 2 && g_fwd_impl != 1) {
+        const int rc = ngp::mlp_fwd_v2_launch(emb, dirs, w, sigmas, rgbs, save, n, n_dev, st);
+        if (rc != -2) return rc;   // -2: not applicable (tiny n / no tensor-map entry point) -> v1 below
+        if (g_fwd_impl == 2 && n >= kTile) return -1;   // explicitly requested: do not fall back silently
+    }
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel<TEmb>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -854,6 +701,13 @@ extern "C" int ngp_debug_mlp_trace(long long* out_host) {
 #endif
 
 extern "C" {
+
+int ngp_mlp_set_impl(int fwd_impl) {
+    NGP_REQUIRE(fwd_impl >= 0 && fwd_impl <= 2, "fwd_impl must be 0 (auto), 1 (v1) or 2 (v2)");
+    const char* e = getenv("NGP_MLP_FWD");   // an explicit environment override wins (A/B runs of unmodified scripts)
+    g_fwd_impl = e ? atoi(e) : fwd_impl;
+    return 0;
+}
 
 int64_t ngp_mlp_save_bytes(int64_t n) {
     // [n x 16] fp16 h (sigma-net output) + [n x 4] fp16 rgb (3 used): with them the backward skips layers 2 and 5
