@@ -669,10 +669,13 @@ int g_fwd_impl = 0;
 template <typename TEmb>
 int launch_fwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, float* sigmas, void* rgbs, void* save,
                int64_t n, const int32_t* n_dev, cudaStream_t st) {
-    if (sizeof(TEmb) == 2 && g_fwd_impl != 1) {
+    // the environment variable NGP_MLP_FWD overrides ngp_mlp_set_impl (A/B runs of unmodified scripts)
+    static const int env_impl = [] { const char* e = getenv("NGP_MLP_FWD"); return e ? atoi(e) : -1; }();
+    const int impl = env_impl >= 0 ? env_impl : g_fwd_impl;
+    if (sizeof(TEmb) == 2 && impl != 1) {
         const int rc = ngp::mlp_fwd_v2_launch(emb, dirs, w, sigmas, rgbs, save, n, n_dev, st);
         if (rc != -2) return rc;   // -2: not applicable (tiny n / no tensor-map entry point) -> v1 below
-        if (g_fwd_impl == 2 && n >= kTile) return -1;   // explicitly requested: do not fall back silently
+        if (impl == 2 && n >= kTile) return -1;   // explicitly requested: do not fall back silently
     }
     static bool configured = false;
     if (!configured) {
@@ -704,8 +707,7 @@ extern "C" {
 
 int ngp_mlp_set_impl(int fwd_impl) {
     NGP_REQUIRE(fwd_impl >= 0 && fwd_impl <= 2, "fwd_impl must be 0 (auto), 1 (v1) or 2 (v2)");
-    const char* e = getenv("NGP_MLP_FWD");   // an explicit environment override wins (A/B runs of unmodified scripts)
-    g_fwd_impl = e ? atoi(e) : fwd_impl;
+    g_fwd_impl = fwd_impl;
     return 0;
 }
 
