@@ -113,14 +113,27 @@ class SyntheticLego:
             self.rays = torch.rand(len(self.poses), n_pix, 3, device=dev, generator=g)
         return self.rays
 
+    def _draw(self, idx, n, dev):
+        """(image index, pixel index) of a training batch: datasets/base.py:34-52 ('all_images': every ray from a
+        random image; 'same_image': all rays of the batch from image ``idx``)."""
+        if self._gen is None or self._gen.device != dev:
+            self._gen = torch.Generator(device=dev).manual_seed(self._seed)
+        if self.ray_sampling_strategy == 'same_image':
+            img = torch.full((n,), int(idx) % len(self.poses), device=dev, dtype=torch.long)
+        elif self.ray_sampling_strategy == 'all_images':
+            img = torch.randint(0, len(self.poses), (n,), device=dev, generator=self._gen)
+        else:
+            raise ValueError(f"unknown ray_sampling_strategy {self.ray_sampling_strategy!r}")
+        pix = torch.randint(0, self.img_wh[0] * self.img_wh[1], (n,), device=dev, generator=self._gen)
+        return img, pix
+
     def __getitem__(self, idx):
         dev = self.poses.device
         if self._gen is None or self._gen.device != dev:
             self._gen = torch.Generator(device=dev).manual_seed(self._seed)
         n = self.batch_size
         if self.split.startswith('train'):
-            img = torch.randint(0, len(self.poses), (n,), device=dev, generator=self._gen)
-            pix = torch.randint(0, self.img_wh[0] * self.img_wh[1], (n,), device=dev, generator=self._gen)
+            img, pix = self._draw(idx, n, dev)
             sample = {'img_idxs': img, 'pix_idxs': pix, 'pose': self.poses[img], 'direction': self.directions[pix]}
             if self.with_rgb:
                 if self.scene == 'analytic':

@@ -1,5 +1,5 @@
-"""Viewer entry point — mirrors the reference's gui.py: OrbitCamera (:28-74) and
-NGPGUI(hparams, model_config, K, img_wh, poses, radius).render_cam() (:77-145).  The Taichi GGUI window
+"""Viewer entry point — same entry points as the reference's gui.py: an OrbitCamera rig (role of :28-74, written
+from scratch) and NGPGUI(hparams, model_config, K, img_wh, poses, radius).render_cam() (:77-145).  The Taichi GGUI window
 (Vulkan) is out of scope: render() drives the same per-frame path headlessly
 along an orbit and writes PNG frames instead of presenting them."""
 import os
@@ -17,54 +17,72 @@ from modules.utils import depth2img
 warnings.filterwarnings("ignore")
 
 
-def _rotvec_to_matrix(v):
-    """Rodrigues formula (the reference uses scipy.spatial.transform.Rotation.from_rotvec)."""
-    theta = np.linalg.norm(v)
-    if theta < 1e-12:
+def _axis_angle(axis, angle):
+    """Rotation by ``angle`` radians about ``axis`` (Rodrigues; the reference goes through scipy's Rotation)."""
+    n = float(np.linalg.norm(axis))
+    if n < 1e-12 or angle == 0.0:
         return np.eye(3)
-    k = v / theta
-    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
-    return np.eye(3) + np.sin(theta) * K + (1 - np.cos(theta)) * (K @ K)
+    x, y, z = np.asarray(axis, dtype=np.float64) / n
+    c, s = np.cos(angle), np.sin(angle)
+    C = 1.0 - c
+    return np.array([[c + x * x * C, x * y * C - z * s, x * z * C + y * s],
+                     [y * x * C + z * s, c + y * y * C, y * z * C - x * s],
+                     [z * x * C - y * s, z * y * C + x * s, c + z * z * C]])
 
 
 class OrbitCamera:
+    """Camera rig of the viewer (role of the reference's gui.py:28-74): an orientation, a look-at offset and an
+    orbit distance; ``pose`` is the 4x4 camera-to-world matrix render_cam() consumes.  The camera sits ``distance``
+    behind the pivot along its own viewing axis; dragging rotates about the camera's current up / right axes, the
+    wheel scales the distance geometrically, panning shifts the pivot in the camera frame."""
+    DRAG_DEG_PER_UNIT = 80.0       # degrees of rotation per unit of normalised mouse travel
+    ZOOM_BASE = 1.1
+    PAN_GAIN = 1e-4
+
     def __init__(self, K, img_wh, poses, r):
         self.K = K
         self.W, self.H = img_wh
-        self.radius = r
-        self.center = np.zeros(3)
-        pose_np = poses.cpu().numpy()
-        self.rot = pose_np[0][:3, :3]  # initial rotation = first training pose
-        self.rotate_speed = 0.8
-        self.res_defalut = pose_np[0]
+        self.distance = float(r)
+        self.pivot = np.zeros(3)
+        first = poses[0].detach().cpu().numpy() if torch.is_tensor(poses) else np.asarray(poses[0])
+        self.home = first.copy()                    # the first training pose: initial orientation
+        self.orientation = first[:3, :3].astype(np.float64).copy()
+
+    # the rest of the viewer reads these two names
+    @property
+    def radius(self):
+        return self.distance
+
+    @property
+    def rot(self):
+        return self.orientation
 
     @property
     def pose(self):
-        res = np.eye(4)
-        res[2, 3] -= self.radius       # move the camera back to the orbit radius
-        rot = np.eye(4)
-        rot[:3, :3] = self.rot
-        res = rot @ res
-        res[:3, 3] -= self.center
-        return res
+        eye_in_cam = np.array([0.0, 0.0, -self.distance])        # back off along the viewing (+z) axis
+        c2w = np.eye(4)
+        c2w[:3, :3] = self.orientation
+        c2w[:3, 3] = self.orientation @ eye_in_cam - self.pivot
+        return c2w
 
     def reset(self, pose=None):
-        self.rot = np.eye(3)
-        self.center = np.zeros(3)
-        self.radius = 2.0
+        self.pivot = np.zeros(3)
+        self.distance = 2.0
+        self.orientation = np.eye(3)
         if pose is not None:
-            self.rot = pose.cpu().numpy()[:3, :3]
+            m = pose.detach().cpu().numpy() if torch.is_tensor(pose) else np.asarray(pose)
+            self.orientation = m[:3, :3].astype(np.float64).copy()
 
     def orbit(self, dx, dy):
-        rx = self.rot[:, 1] * np.radians(100 * self.rotate_speed * dx)
-        ry = self.rot[:, 0] * np.radians(-100 * self.rotate_speed * dy)
-        self.rot = _rotvec_to_matrix(ry) @ _rotvec_to_matrix(rx) @ self.rot
+        yaw = _axis_angle(self.orientation[:, 1], np.radians(self.DRAG_DEG_PER_UNIT * dx))
+        pitch = _axis_angle(self.orientation[:, 0], np.radians(-self.DRAG_DEG_PER_UNIT * dy))
+        self.orientation = pitch @ yaw @ self.orientation
 
     def scale(self, delta):
-        self.radius *= 1.1 ** (-delta)
+        self.distance /= self.ZOOM_BASE ** delta
 
     def pan(self, dx, dy, dz=0):
-        self.center += 1e-4 * self.rot @ np.array([dx, dy, dz])
+        self.pivot = self.pivot + self.PAN_GAIN * (self.orientation @ np.array([dx, dy, dz], dtype=np.float64))
 
 
 class NGPGUI:

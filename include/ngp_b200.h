@@ -162,16 +162,19 @@ int ngp_mlp_fwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp
 int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
                     const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n_max,
                     const int32_t* n_dev, void* stream);
-/* Adam with the per-step scalars in device memory: hyper_dev = {lr/(1-beta1^t), sqrt(1-beta2^t), inv_scale}
- * (so the launch arguments are step-invariant and the launch can live in a CUDA graph). */
+/* Adam with the per-step scalars in device memory: hyper_dev[4] = {lr/(1-beta1^t), sqrt(1-beta2^t), inv_scale,
+ * t (Adam's applied-step count, int bits)} (so the launch arguments are step-invariant and the launch can live in a
+ * CUDA graph). */
 int ngp_adam_step_dyn(float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* param_f16_or_null,
                       const int32_t* found_inf_or_null, const float* hyper_dev, float beta1, float beta2,
                       float eps, int zero_grad, int64_t n, void* stream);
-/* Advances the device-side step counter and writes hyper_dev for ngp_adam_step_dyn:
- * lr = cosine annealing from lr0 to lr_min over max_steps (train.py:159-163) evaluated at the 0-based step,
- * Adam bias corrections for t = step+1 (train.py:143-156). */
+/* Advances the device-side iteration counter and writes hyper_dev for ngp_adam_step_dyn:
+ * lr = cosine annealing from lr0 to lr_min over max_steps (train.py:159-163) evaluated at the 0-based iteration
+ * (scheduler.step() runs every iteration, train.py:201); Adam bias corrections (train.py:143-156) for t = number of
+ * APPLIED steps: t advances only when *found_inf == 0 (GradScaler.step skips optimizer.step() on inf/NaN, :199). */
 int ngp_adam_hyper_update(int32_t* step_dev, float lr0, float lr_min, int32_t max_steps, float beta1,
-                          float beta2, float inv_scale, float* hyper_dev, void* stream);
+                          float beta2, float inv_scale, const int32_t* found_inf_or_null, float* hyper_dev,
+                          void* stream);
 /* torch.cuda.amp.GradScaler.update() on the device (train.py:137-141,200): state_dev = {scale, growth_tracker};
  * found_inf != 0 -> scale *= backoff, tracker = 0; else tracker += 1 and, every growth_interval clean steps,
  * scale *= growth.  Also refreshes hyper_dev[2] = 1 / (scale * world_size) for the NEXT step's Adam. */

@@ -22,7 +22,7 @@ def render(model, rays_o, rays_d, test_time=False, exp_step_factor=0, T_threshol
     rays_d = rays_d.contiguous()
     hits_t = ray_aabb_intersection(rays_o, rays_d, model.scale)
     if test_time:
-        if getattr(model, '_fusable', None) is not None and model._fusable(rays_o) and not _FORCE_LOOP:
+        if getattr(model, '_fusable', None) is not None and rays_o.is_cuda and not _FORCE_LOOP:
             # same result as the incremental loop below, without its per-iteration host syncs
             from taichi_nerfs_b200.render_frame import render_frame
             return render_frame(model, rays_o, rays_d, exp_step_factor, T_threshold, max_samples)

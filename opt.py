@@ -7,8 +7,10 @@ import argparse
 _FLAGS = [
     # dataset parameters
     ('--root_dir', dict(type=str, default='', help='root directory of dataset (unused by the synthetic dataset)')),
-    ('--dataset_name', dict(type=str, default='synthetic', choices=['synthetic', 'nerf', 'nsvf', 'colmap', 'ngp'],
-                            help='which dataset to train/test (disk loaders are out of scope offline)')),
+    ('--dataset_name', dict(type=str, default='synthetic', choices=['synthetic', 'teacher'],
+                            help='synthetic: analytic scene; teacher: views of the reference\'s shipped trained Lego '
+                                 'model.  The disk loaders nerf/nsvf/colmap/ngp of the reference are out of scope '
+                                 '(SURVEY.md §2.1; no dataset exists offline) and are rejected here')),
     ('--split', dict(type=str, default='train', choices=['train', 'trainval', 'trainvaltest'],
                      help='use which split to train')),
     ('--downsample', dict(type=float, default=1.0, help='downsample factor (<=1.0) for the images')),
@@ -16,7 +18,8 @@ _FLAGS = [
     ('--model_name', dict(type=str, default='ngp', choices=['ngp'], help='which model to train/test')),
     ('--scale', dict(type=float, default=0.5, help='scene scale (whole scene must lie in [-scale, scale]^3')),
     ('--half_opt', dict(action='store_true', default=False, help='whether to use half optimization')),
-    ('--encoder_type', dict(type=str, default='hash', choices=['hash', 'triplane'], help='which encoder to use')),
+    ('--encoder_type', dict(type=str, default='hash', choices=['hash'],
+                        help='which encoder to use (the reference\'s experimental triplane encoder is out of scope)')),
     ('--sh_degree', dict(type=int, default=2, help='degree of spherical harmonics (svox only; unused)')),
     ('--grid_size', dict(type=int, default=256, help='size of voxel grid in each dimension (svox only; unused)')),
     ('--grid_radius', dict(type=float, default=0.0125, help='radius of voxel grid points (svox only; unused)')),

@@ -1193,3 +1193,22 @@ int ngp_raymarching_lanes_cpu(const float* rays_o, const float* rays_d, const fl
     stats[1] = n_gen;
     return 0;
 }
+
+/* ---- host thread control for the timed CPU arms (bench.py cpu_baseline / --impl reference) --------------------
+ * torchrun exports OMP_NUM_THREADS=1 to its workers; the baseline must use the cores it reports. */
+extern void omp_set_num_threads(int);
+extern int omp_get_max_threads(void);
+int ngp_oracle_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+int ngp_oracle_threads_used(void) {
+    int n = 0;
+#pragma omp parallel
+    {
+#pragma omp atomic
+        n += 1;
+    }
+    return n;
+}
+

@@ -44,6 +44,13 @@ def lib():
     return _lib
 
 
+def set_threads(n: int) -> int:
+    """Force the OpenMP team size (torchrun exports OMP_NUM_THREADS=1) and return the number of threads a parallel
+    region REALLY runs with (counted, not assumed)."""
+    lib().ngp_oracle_set_threads(int(n))
+    return int(lib().ngp_oracle_threads_used())
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

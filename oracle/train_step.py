@@ -13,9 +13,10 @@ import numpy as np
 from . import oracle as O
 
 
-def make_rays(n, seed=0, radius=1.4, img=800, focal=1111.111):
+def make_rays(n, seed=0, radius=1.4, img=800, focal=1111.111, img_h=None):
     """Lego-shape synthetic rays (numpy): pinhole 800x800 fx=fy=1111.111 (datasets/nsvf.py:37-44), cameras on
-    the upper hemisphere looking at the origin, [right, down, front] convention (datasets/ray_utils.py:8-80)."""
+    the upper hemisphere looking at the origin, [right, down, front] convention (datasets/ray_utils.py:8-80).
+    ``img`` x ``img_h`` (default square) pixels."""
     rng = np.random.default_rng(seed)
     th = rng.uniform(0, 2 * np.pi, n)
     ph = np.arccos(rng.uniform(0.05, 0.95, n))
@@ -24,9 +25,10 @@ def make_rays(n, seed=0, radius=1.4, img=800, focal=1111.111):
     right = np.cross(fwd, np.array([0, 0, 1.0]))
     right /= np.linalg.norm(right, axis=-1, keepdims=True)
     down = np.cross(fwd, right)
+    img_h = img if img_h is None else img_h
     u = rng.integers(0, img, n)
-    v = rng.integers(0, img, n)
-    dc = np.stack([(u - img / 2 + .5) / focal, (v - img / 2 + .5) / focal, np.ones(n)], -1)
+    v = rng.integers(0, img_h, n)
+    dc = np.stack([(u - img / 2 + .5) / focal, (v - img_h / 2 + .5) / focal, np.ones(n)], -1)
     d = dc[:, 0:1] * right + dc[:, 1:2] * down + dc[:, 2:3] * fwd
     return c.astype(np.float32), d.astype(np.float32)
 

@@ -75,13 +75,20 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, fl
     }
 }
 
+// hyper = [lr / bc1, sqrt(bc2), inv_scale, Adam step count t (int bits)].  The LR schedule follows the iteration count
+// (scheduler.step() runs every iteration, train.py:199-201) while Adam's bias-correction count t only advances on steps
+// that are applied: GradScaler.step skips optimizer.step() when the gradients hold an inf/NaN.
 __global__ void adam_hyper_kernel(int32_t* __restrict__ step_dev, float lr0, float lr_min, int32_t max_steps, float beta1,
-                                  float beta2, float inv_scale, float* __restrict__ hyper) {
+                                  float beta2, float inv_scale, const int32_t* __restrict__ found_inf,
+                                  float* __restrict__ hyper) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int32_t s = *step_dev;  // 0-based index of the step being taken
+    const int32_t s = *step_dev;  // 0-based index of the iteration being taken
     const double frac = (double)min(s, max_steps) / (double)max(max_steps, 1);
     const double lr = (double)lr_min + ((double)lr0 - (double)lr_min) * (1.0 + cos(3.14159265358979323846 * frac)) / 2.0;
-    const double t = (double)(s + 1);
+    const bool skipped = found_inf != nullptr && *found_inf != 0;
+    const int32_t t_applied = __float_as_int(hyper[3]) + (skipped ? 0 : 1);
+    hyper[3] = __int_as_float(t_applied);
+    const double t = (double)max(t_applied, 1);
     const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
     hyper[0] = (float)(lr / bc1);
     hyper[1] = (float)sqrt(bc2);
@@ -198,10 +205,10 @@ int ngp_adam_step_dyn(float* param, float* grad, float* exp_avg, float* exp_avg_
 }
 
 int ngp_adam_hyper_update(int32_t* step_dev, float lr0, float lr_min, int32_t max_steps, float beta1, float beta2,
-                          float inv_scale, float* hyper_dev, void* stream) {
+                          float inv_scale, const int32_t* found_inf_or_null, float* hyper_dev, void* stream) {
     NGP_REQUIRE(step_dev && hyper_dev, "null pointer");
     adam_hyper_kernel<<<1, 32, 0, ngp::as_stream(stream)>>>(step_dev, lr0, lr_min, max_steps, beta1, beta2, inv_scale,
-                                                            hyper_dev);
+                                                            found_inf_or_null, hyper_dev);
     NGP_LAUNCHED("adam_hyper_kernel");
     return 0;
 }

@@ -60,14 +60,11 @@ class StaticTrainStep:
         self.ws = z(C_)
         self.g_rgb, self.g_op, self.g_depth = z(self.n, 3), z(self.n), z(self.n)
         self.loss_sum = z(1)
-        # optimizer scalars on the device
-        self.step_dev = torch.full((1,), trainer.step_count, device=dev, dtype=i32)
+        # optimizer scalars on the device: owned by the trainer, shared with the module path (NGPTrainer.step)
+        self.step_dev, self.hyper, self.scale_state = trainer.step_dev, trainer.hyper, trainer.scale_state
         self.sample_step = torch.full((1,), trainer.step_count, device=dev, dtype=i32)   # batches drawn so far
-        self.hyper = z(3)
         # GradScaler state on the device: [scale, growth_tracker (int bits)]; growth 2x / 2000 clean steps, backoff 0.5
-        self.dynamic_loss_scale = bool(dynamic_loss_scale)
-        self.scale_state = torch.tensor([trainer.loss_scale, 0.0], device=dev, dtype=f32)
-        self.hyper[2] = parallel.inv_grad_scale(trainer.loss_scale, trainer.world_size)
+        trainer.dynamic_loss_scale = self.dynamic_loss_scale = bool(dynamic_loss_scale)
         self.aabb6 = (C.c_float * 6)(*[float(v) for v in m.xyz_min.flatten().tolist()],
                                      *[float(v) for v in (m.xyz_max - m.xyz_min).flatten().tolist()])
         self._clayout = enc._clayout
@@ -145,41 +142,44 @@ class StaticTrainStep:
                                       _p(self.counter), _p(self.rays_a), _p(self.xyzs), _p(self.dirs),
                                       _p(self.deltas), _p(self.ts), n, cap, st))
 
-    def _enqueue_network(self):
-        L, m, st, n, cap = load(), self.model, self._st(), self.n, self.cap
-        tag = F16 if self.half else F32
-        nd = _p(self.counter)  # counter[0] = number of valid sample rows, read on the device
+    # the five network kernels, one method each (bench.py times them one by one on the buffers of a real step)
+    def _k_hash_fwd(self):
+        L, st, tag = load(), self._st(), (F16 if self.half else F32)
         check(L.ngp_hash_encode_fwd_dyn(_p(self.xyzs), _p(self._table()), C.byref(self._clayout), _p(self.emb), tag,
-                                        cap, nd, self.aabb6, st))
+                                        self.cap, _p(self.counter), self.aabb6, st))
+
+    def _k_mlp_fwd(self):
+        L, st, tag = load(), self._st(), (F16 if self.half else F32)
         check(L.ngp_mlp_fwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.sig), _p(self.rgbs),
-                                _p(self.mlp_save), cap, nd, st))
+                                _p(self.mlp_save), self.cap, _p(self.counter), st))
+
+    def _k_head(self):
         # composite forward + background + MSE + composite backward in one launch (per-ray work)
         bg = 1.0 if self.esf == 0 else 0.0
-        check(L.ngp_ray_head_fused(_p(self.sig), _p(self.rgbs), F16, _p(self.deltas), _p(self.rays_a), _p(self.gt), bg,
-                                   float(self.tr.loss_scale), _p(self.scale_state) if self.dynamic_loss_scale else None,
-                                   self.T_thr, _p(self.loss_sum), _p(self.opacity), _p(self.rgb), _p(self.dsig),
-                                   _p(self.drgbs), n, st))
-        fg = self.tr.flat_grad
-        gw = fg[self.P:self.P + 9408]
-        check(L.ngp_mlp_bwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.mlp_save), _p(self.dsig),
-                                _p(self.drgbs), _p(self.demb), _p(gw), cap, nd, st))
-        check(L.ngp_hash_encode_bwd_dyn(_p(self.xyzs), _p(self.demb), tag, C.byref(self._clayout), _p(fg), cap, nd,
-                                        self.aabb6, st))
+        check(load().ngp_ray_head_fused(_p(self.sig), _p(self.rgbs), F16, _p(self.deltas), _p(self.rays_a), _p(self.gt),
+                                        bg, float(self.tr.loss_scale),
+                                        _p(self.scale_state) if self.dynamic_loss_scale else None, self.T_thr,
+                                        _p(self.loss_sum), _p(self.opacity), _p(self.rgb), _p(self.dsig),
+                                        _p(self.drgbs), self.n, self._st()))
 
-    def _enqueue_optimizer(self):
-        L, tr, st = load(), self.tr, self._st()
-        fg = tr.flat_grad
-        check(L.ngp_check_finite(_p(fg), fg.numel(), _p(tr.found_inf), st))
-        # inv_scale: static (host constant) or the device value maintained by ngp_loss_scale_update (-1 sentinel)
-        inv = -1.0 if self.dynamic_loss_scale else parallel.inv_grad_scale(tr.loss_scale, tr.world_size)
-        check(L.ngp_adam_hyper_update(_p(self.step_dev), tr.lr0, tr.lr0 / 30, tr.max_steps, tr.betas[0], tr.betas[1],
-                                      inv, _p(self.hyper), st))
-        # one launch over [hash table | MLP weights] (the trainer keeps parameters, moments and gradients flat)
-        check(L.ngp_adam_step_dyn(_p(tr.flat_param), _p(fg), _p(tr.exp_avg), _p(tr.exp_avg_sq), _p(tr._shadow_full),
-                                  _p(tr.found_inf), _p(self.hyper), tr.betas[0], tr.betas[1], tr.eps, 1, fg.numel(), st))
-        if self.dynamic_loss_scale:  # GradScaler.update(): adjusts the scale used by the NEXT step
-            check(L.ngp_loss_scale_update(_p(self.scale_state), _p(tr.found_inf), 2.0, 0.5, 2000, float(tr.world_size),
-                                          _p(self.hyper), st))
+    def _k_mlp_bwd(self):
+        L, st, tag = load(), self._st(), (F16 if self.half else F32)
+        gw = self.tr.flat_grad[self.P:self.P + 9408]
+        check(L.ngp_mlp_bwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.mlp_save), _p(self.dsig),
+                                _p(self.drgbs), _p(self.demb), _p(gw), self.cap, _p(self.counter), st))
+
+    def _k_hash_bwd(self):
+        L, st, tag = load(), self._st(), (F16 if self.half else F32)
+        check(L.ngp_hash_encode_bwd_dyn(_p(self.xyzs), _p(self.demb), tag, C.byref(self._clayout),
+                                        _p(self.tr.flat_grad), self.cap, _p(self.counter), self.aabb6, st))
+
+    def _enqueue_network(self):
+        # counter[0] = number of valid sample rows, read on the device by every kernel
+        self._k_hash_fwd()
+        self._k_mlp_fwd()
+        self._k_head()
+        self._k_mlp_bwd()
+        self._k_hash_bwd()
 
     def _enqueue_sampler(self):
         """datasets/base.py:34-61 + ray_utils.py:51-80 + the marching jitter, keyed by (seed, batch counter, ray)."""
@@ -190,9 +190,7 @@ class StaticTrainStep:
                                           _p(self.gt), _p(self.noise), None, None, self.n, self._st()))
 
     def _enqueue_update(self):
-        if self.tr.world_size > 1:
-            parallel.allreduce_gradients(self.tr.flat_grad, self.tr.pg)
-        self._enqueue_optimizer()
+        self.tr.enqueue_update()   # [all-reduce] -> check_finite -> LR/bias scalars -> fused Adam -> GradScaler.update
 
     def _enqueue(self, sampled=False, mode="sync"):
         if sampled:

@@ -32,8 +32,10 @@ def render_frame(model, rays_o, rays_d, exp_step_factor=0.0, T_threshold=1e-4, m
     opacity = torch.empty(n, device=dev, dtype=torch.float32)
     enc = model.pos_encoder
     half = hasattr(enc, "table_f16")
-    table = enc.table_f16() if half else enc.hash_table.detach().contiguous()
-    W = [w.detach() for w in mlp_weights(model)]
+    fused = bool(model._fusable(rays_o))     # stock architecture: hash + tcgen05 MLP kernels on the raw sample rows
+    if fused:
+        table = enc.table_f16() if half else enc.hash_table.detach().contiguous()
+        W = [w.detach() for w in mlp_weights(model)]
     aabb = model.xyz_min.flatten().tolist() + (model.xyz_max - model.xyz_min).flatten().tolist()
     total = 0
     zeros = torch.zeros(min(block_rays, n), device=dev, dtype=torch.float32)  # test-time march has no jitter
@@ -80,8 +82,14 @@ def render_frame(model, rays_o, rays_d, exp_step_factor=0.0, T_threshold=1e-4, m
             depth[b:e] = 0
             rgb[b:e] = 0
             continue
-        emb = ops.hash_encode_fwd(xyzs, table, enc._clayout, enc.out_dim, aabb=aabb)  # normalisation in-kernel
-        sigmas, rgbs = ops.mlp_fwd(emb, dirs, W)
+        if fused:
+            emb = ops.hash_encode_fwd(xyzs, table, enc._clayout, enc.out_dim, aabb=aabb)  # normalisation in-kernel
+            sigmas, rgbs = ops.mlp_fwd(emb, dirs, W)
+        else:   # any other NGP configuration (e.g. the reference's L=4 F=4 deployment model): module forward
+            with torch.autocast('cuda', dtype=torch.float16):
+                outs = [model(xyzs[i:i + (1 << 21)], dirs[i:i + (1 << 21)]) for i in range(0, S, 1 << 21)]
+            sigmas = torch.cat([o[0] for o in outs]).float().contiguous()
+            rgbs = torch.cat([o[1] for o in outs]).contiguous()
         _, op_b, dp_b, rgb_b, _ = ops.composite_train_fwd(sigmas, rgbs, deltas, ts, rays_a, T_threshold)
         opacity[b:e] = op_b
         depth[b:e] = dp_b

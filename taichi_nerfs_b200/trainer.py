@@ -1,10 +1,12 @@
 """Training step of the NGP hot path (the body of the reference's loop, train.py:168-201):
 get_rays -> render -> MSE -> backward -> [gradient all-reduce] -> optimizer step.
 
-``NGPTrainer.step`` keeps the reference's numerics (torch.autocast(fp16), loss scaling as
-GradScaler(2**16 | 2**19), Adam(eps=1e-15), cosine LR to lr/30) but replaces
-optimizer.zero_grad + GradScaler.unscale_/inf-check + Adam + the fp16 table re-cast by ONE fused pass
-per parameter (csrc/optim.cu) and never synchronises the host for the inf check.
+``NGPTrainer.step`` keeps the reference's numerics (torch.autocast(fp16), GradScaler(2**16 | 2**19) with its
+dynamic scale: x0.5 on inf/NaN, x2 every 2000 clean steps, skipped steps do not advance Adam's step count;
+Adam(eps=1e-15), cosine LR to lr/30) but replaces optimizer.zero_grad + GradScaler.unscale_/inf-check + Adam +
+the fp16 table re-cast by ONE fused pass over the flat parameter buffer (csrc/optim.cu).  The scale, the LR /
+bias-correction scalars and the iteration counter live in device memory (``scale_state``, ``hyper``, ``step_dev``),
+so nothing synchronises the host; the graph-captured step (fast_step.py) enqueues exactly the same kernels.
 
 Multi-GPU: rays are sharded across ranks (each rank renders its own batch); the only collective is
 one all-reduce (sum) of the flat gradient buffer per step, folded into the fused Adam as inv_scale /
@@ -12,17 +14,23 @@ world_size.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import torch
 import torch.nn.functional as F
 
 from . import ops, parallel
+from ._lib import check, load
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
 
 
 class NGPTrainer:
     def __init__(self, model, lr: float = 1e-2, max_steps: int = 20000, loss_scale: float | None = None,
-                 betas=(0.9, 0.999), eps: float = 1e-15, process_group=None):
+                 betas=(0.9, 0.999), eps: float = 1e-15, process_group=None, dynamic_loss_scale: bool = True):
         self.model = model
         self.lr0 = lr
         self.max_steps = max_steps
@@ -60,6 +68,14 @@ class NGPTrainer:
             if p is getattr(model.pos_encoder, 'hash_table', None):
                 model.pos_encoder.grad_sink = self.flat_grad[off - s - q:off - q]
         self.found_inf = torch.zeros(1, device=dev, dtype=torch.int32)
+        # device-side optimizer scalars (shared with StaticTrainStep): iteration counter, [lr/bc1, sqrt(bc2), 1/(scale*world),
+        # Adam step count], GradScaler state [scale, growth tracker]
+        self.dynamic_loss_scale = bool(dynamic_loss_scale)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.hyper = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.hyper[2] = parallel.inv_grad_scale(self.loss_scale, self.world_size)
+        self.scale_state = torch.tensor([self.loss_scale, 0.0], device=dev, dtype=torch.float32)
+        self._views = [(p, p.data_ptr(), p.grad.data_ptr()) for p in self.params]
         self._shadow = self._shadow_full = None
         enc = model.pos_encoder
         if hasattr(enc, "adopt_shadow"):
@@ -74,6 +90,26 @@ class NGPTrainer:
         eta_min = self.lr0 / 30
         return eta_min + (self.lr0 - eta_min) * (1 + math.cos(math.pi * min(step, self.max_steps) / self.max_steps)) / 2
 
+    def check_aliasing(self):
+        """The fused optimizer updates parameters through the flat buffers: every nn.Parameter must still be the view
+        created in __init__ (model.to()/half(), zero_grad(set_to_none=True) or a foreign optimizer break that)."""
+        for p, dptr, gptr in self._views:
+            if p.data_ptr() != dptr or p.grad is None or p.grad.data_ptr() != gptr:
+                raise RuntimeError("NGPTrainer: a parameter or its .grad no longer aliases the flat buffers (was the "
+                                   "model moved / cast, or its gradients set to None?) — build a new NGPTrainer")
+
+    def detach(self):
+        """Give the model ordinary, independent parameters again (e.g. before handing it to a torch optimizer)."""
+        for p in self.params:
+            p.data = p.data.clone()
+            p.grad = None
+        enc = self.model.pos_encoder
+        if hasattr(enc, 'grad_sink'):
+            enc.grad_sink = None
+        if self._shadow is not None and hasattr(enc, 'adopt_shadow'):
+            enc.adopt_shadow(None)
+        self._views = []
+
     def forward_backward(self, rays_o, rays_d, rgb_gt, exp_step_factor=0.0, extra_loss=None):
         from modules.rendering import render
         with torch.autocast(device_type='cuda', dtype=torch.float16):
@@ -81,19 +117,35 @@ class NGPTrainer:
             loss = F.mse_loss(results['rgb'], rgb_gt)
             if extra_loss is not None:  # e.g. distortion loss (train.py:194-195)
                 loss = loss + extra_loss(results)
-        (loss * self.loss_scale).backward()
+        # GradScaler.scale(loss): the current scale is a device scalar, no host read
+        scale = self.scale_state[0] if self.dynamic_loss_scale else self.loss_scale
+        (loss * scale).backward()
         return loss, results
 
+    def enqueue_update(self):
+        """[all-reduce] -> inf check -> LR / bias-correction scalars -> fused Adam (+fp16 shadow, grad zero) ->
+        GradScaler.update(), all on the current stream with device-side scalars (graph-capturable)."""
+        L, st = load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        fg = self.flat_grad
+        parallel.allreduce_gradients(fg, self.pg)
+        check(L.ngp_check_finite(_p(fg), fg.numel(), _p(self.found_inf), st))   # after the sum: identical on every rank
+        # inv_scale: static (host constant) or the device value maintained by ngp_loss_scale_update (-1 sentinel)
+        inv = -1.0 if self.dynamic_loss_scale else parallel.inv_grad_scale(self.loss_scale, self.world_size)
+        check(L.ngp_adam_hyper_update(_p(self.step_dev), self.lr0, self.lr0 / 30, self.max_steps, self.betas[0],
+                                      self.betas[1], inv, _p(self.found_inf), _p(self.hyper), st))
+        # one launch over [hash table | MLP weights]
+        check(L.ngp_adam_step_dyn(_p(self.flat_param), _p(fg), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                  _p(self._shadow_full), _p(self.found_inf), _p(self.hyper), self.betas[0],
+                                  self.betas[1], self.eps, 1, fg.numel(), st))
+        if self.dynamic_loss_scale:  # GradScaler.update(): adjusts the scale used by the NEXT step
+            check(L.ngp_loss_scale_update(_p(self.scale_state), _p(self.found_inf), 2.0, 0.5, 2000,
+                                          float(self.world_size), _p(self.hyper), st))
+
     def optimizer_step(self):
+        self.check_aliasing()
         self.step_count += 1
-        parallel.allreduce_gradients(self.flat_grad, self.pg)
         self.found_inf.zero_()
-        ops.check_finite(self.flat_grad, self.found_inf)  # after the sum: identical on every rank
-        lr = self.lr_at(self.step_count - 1)
-        inv = parallel.inv_grad_scale(self.loss_scale, self.world_size)
-        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, lr, self.step_count,
-                      self.betas[0], self.betas[1], self.eps, inv, param_f16=self._shadow_full,
-                      found_inf=self.found_inf, zero_grad=True)
+        self.enqueue_update()
         if self._shadow is not None:
             self.model.pos_encoder.adopt_shadow(self._shadow)
 

@@ -45,3 +45,16 @@ def test_ctypes_mirror_size():
     assert ctypes.sizeof(CHashLayout) == 16 + 4 * 16 * 4
     cl = make_hash_layout(2 ** 19, 16, 16, 1024, 2).as_ctypes()
     assert cl.n_levels == 16 and cl.offsets[15] == 5185744 and cl.map_sizes[0] == 4096
+
+
+def test_synthetic_dataset_sampling_strategies():
+    """datasets/base.py:34-52: 'all_images' draws an image per ray, 'same_image' takes every ray from image idx."""
+    import torch
+    from datasets.synthetic import SyntheticLego
+    ds = SyntheticLego(n_images=7, img_wh=(40, 30), focal=50.0, batch_size=256)
+    b = ds[3]
+    assert b['rgb'].shape == (256, 3) and len(torch.unique(b['img_idxs'])) > 1
+    ds.ray_sampling_strategy = 'same_image'
+    b = ds[3]
+    assert bool((b['img_idxs'] == 3).all()) and int(b['pix_idxs'].max()) < 1200
+    assert torch.equal(b['pose'], ds.poses[3].expand(256, 3, 4))

@@ -639,3 +639,21 @@ def test_chunked_fast_path_emulation_equals_reference_march(oracle, lego_bitfiel
             assert np.array_equal(counts, ra[:, 2])
             assert np.array_equal(ts2.view(np.uint32), ts.view(np.uint32))
             assert st["regular_chunks"] > 8 * st["general_chunks"]
+
+
+# ---- fast_hash / under_hash known-answer test (Python-int arithmetic, tests/hash_kat.py) -------------------
+@pytest.mark.parametrize("max_res", [1024, 4096])
+def test_hash_index_known_answers(oracle, max_res):
+    """The oracle's corner indices / weights against hash_encoder.py:43-71,108-139 evaluated with Python integers:
+    a table that stores its own entry index makes the encoder output reveal every index it touched."""
+    import hash_kat as K
+    from taichi_nerfs_b200.layout import make_hash_layout
+    lay = make_hash_layout(2 ** 19, 16, 16, max_res, 2)
+    if max_res == 1024:
+        for p, level, corner, entry in K.hand_computed_vectors():
+            assert K.corner_table(lay, p, level)[corner][0] == entry
+    table = K.index_table(lay)
+    want = K.expected(lay, K.POINTS)
+    got = oracle.hash_encode_fwd(K.POINTS, table.reshape(-1), lay).astype(np.float64)
+    # outputs are O(index) ~ 5e6; a wrong index is off by >= 1 * weight, fp32 summation slack is ~1e-7 relative
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=0.5)

@@ -67,6 +67,9 @@ def main(prefix_args=None):
                             seed=seed, **extra).to(device)
     train_dataset.batch_size = hparams.batch_size
     train_dataset.ray_sampling_strategy = hparams.ray_sampling_strategy
+    if hparams.random_bg:
+        raise SystemExit("--random_bg applies to real scenes with an alpha channel (datasets/colmap.py of the "
+                         "reference), which are out of scope here (SURVEY.md §2.1)")
     train_dataset._seed = seed + rank  # different rays per rank
     test_dataset = dataset(root_dir=hparams.root_dir, split='test', downsample=hparams.downsample,
                            n_images=4, **extra).to(device)
