@@ -108,7 +108,9 @@ int ngp_raymarching_train_write(const float* rays_o, const float* rays_d, const 
  * noise != NULL: training semantics (ray_march.py:36-43).  Every ray marches
  * once, reserves its rows with one atomicAdd on counter[0] (caller zeroes counter[0..1]) and writes
  * rays_a[r] = (r, start, n) + its samples.  Row order across rays is arbitrary (as in the reference,
- * ray_march.py:76-81); rays that do not fit `capacity` are dropped and counted in counter[1]. */
+ * ray_march.py:76-81); the one ray that straddles the end of the
+ * `capacity` buffers keeps the samples that fit (rendered truncated), rays reserving after it own no rows; both kinds
+ * are counted in counter[1], and every row below min(counter[0], capacity) is written. */
 int ngp_raymarching_frame(const float* rays_o, const float* rays_d, const float* hits_t, const float* noise,
                           const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
                           float exp_step_factor, int max_samples, int32_t* counter, int32_t* rays_a,
@@ -281,6 +283,28 @@ int ngp_packbits_dev(const float* density_grid, const float* mean_density_dev, f
 /* replaces morton3D_kernel / morton3D_invert_kernel, modules/utils.py:120-154 */
 int ngp_morton3d(const int32_t* coords, int32_t* indices, int64_t n, void* stream);
 int ngp_morton3d_invert(const int32_t* indices, int32_t* coords, int64_t n, void* stream);
+
+/* ---- fused occupancy-grid update ------------------------------------------------------
+ * Stage 1 replaces NGP.get_all_cells / sample_uniform_and_occupied_cells (modules/networks.py:168-209: torch.randint,
+ * torch.nonzero + len() host sync, morton3D[_invert] + ti.sync()) and the jittered positions of
+ * update_density_grid (:263-271).  mode 0 (warm-up): every cell of every cascade once, slot i = Morton index i
+ * (per cascade grid_size^3 slots).  mode 1: per cascade M uniformly drawn cells followed by M cells drawn uniformly
+ * among those with density_grid > density_threshold (2M slots; cell_idx = -1 when no cell qualifies).  Randomness:
+ * Philox4x32-10 keyed by `seed`, counter (slot, cascade, step, stream id) - identical on every rank for equal
+ * (seed, step).  Outputs: cell_idx [cascades * slots] (Morton index inside the cascade), xyz [cascades * slots, 3]
+ * world positions.  `workspace`: ngp_grid_workspace_bytes() bytes of caller-owned scratch, 16-byte aligned. */
+int64_t ngp_grid_workspace_bytes(int cascades, int grid_size);
+int ngp_grid_sample_cells(const float* density_grid, int cascades, int grid_size, float scale,
+                          float density_threshold, int mode, int64_t M, uint64_t seed, uint32_t step,
+                          void* workspace, int32_t* cell_idx, float* xyz, void* stream);
+/* Stage 2 (after the caller evaluated `densities` at xyz with the hash + sigma-net kernels) replaces :272-290:
+ * tmp[c, idx] = density (maximum over duplicate picks), density_grid = grid < 0 ? grid : max(grid * decay, tmp)
+ * (count_grid != NULL: erode, decay_i = clamp(decay^(1/count_i), 0.1, 0.95)), *mean_out = mean of the positive cells
+ * (deterministic two-level reduction, no .item()), density_bitfield = packbits(grid > min(mean, density_threshold)). */
+int ngp_grid_update(float* density_grid, const int32_t* cell_idx, const float* densities, int64_t slots_per_cascade,
+                    int cascades, int grid_size, const float* count_grid_or_null, float decay,
+                    float density_threshold, void* workspace, float* mean_out, uint8_t* density_bitfield,
+                    void* stream);
 
 /* ---- training ray batch sampling ------------------------ */
 /* replaces, per step: BaseDataset.__getitem__ (datasets/base.py:34-61: torch.randint x2 + gathers of

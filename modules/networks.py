@@ -187,7 +187,61 @@ class NGP(nn.Module):
 
     @torch.no_grad()
     def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False):
-        """EMA-max update of the density grid + re-pack of the bitfield (networks.py:255-290)."""
+        """EMA-max update of the density grid + re-pack of the bitfield (networks.py:255-290) as one fixed chain of
+        launches: [occupied-cell scan] -> cell pick + jittered positions -> hash + sigma net -> scatter-max -> EMA +
+        partial sums -> mean -> packbits.  No torch.nonzero / len() / .item(): nothing synchronises the host, and the
+        Philox-keyed draws make the grids of all ranks identical (same seed and update counter, replicated
+        parameters) without a broadcast."""
+        from taichi_nerfs_b200 import ops
+        grid = self.density_grid
+        if not grid.is_cuda:
+            raise RuntimeError("update_density_grid runs on the CUDA path only (no CPU fallback)")
+        if not grid.is_contiguous():
+            self.density_grid = grid = grid.contiguous()
+        ws = self.__dict__.get('_grid_ws')
+        if ws is None or ws.device != grid.device:
+            ws = self.__dict__['_grid_ws'] = ops.grid_workspace(self.cascades, self.grid_size, grid.device)
+            self.__dict__['_grid_mean'] = torch.zeros(1, device=grid.device, dtype=torch.float32)
+        step = self.__dict__.get('_grid_step', 0)
+        self.__dict__['_grid_step'] = step + 1
+        cell_idx, xyzs_w = ops.grid_sample_cells(grid, self.scale, density_threshold, warmup, self.grid_size ** 3 // 4,
+                                                 self.grid_seed, step, ws)
+        densities = self._density_eval(xyzs_w)
+        count = None
+        if erode:
+            count = self.count_grid.contiguous()
+        ops.grid_update(grid, cell_idx, densities, density_threshold, decay, ws, self.__dict__['_grid_mean'],
+                        self.density_bitfield, count_grid=count)
+
+    def _density_eval(self, xyzs_w):
+        """sigma at world positions for the grid update: hash encode (AABB normalisation folded into the kernel) +
+        sigma net, straight on the kernels for the stock architecture, NGP.density otherwise."""
+        if not self._fusable(xyzs_w):
+            return self.density(xyzs_w).float().contiguous()
+        from taichi_nerfs_b200 import ops
+        from taichi_nerfs_b200.fused_mlp import mlp_weights
+        enc = self.pos_encoder
+        table = enc.table_f16() if hasattr(enc, 'table_f16') else enc.hash_table.detach().contiguous()
+        aabb = self.__dict__.get('_aabb6')
+        if aabb is None:
+            aabb = self.__dict__['_aabb6'] = (self.xyz_min.flatten().tolist()
+                                               + (self.xyz_max - self.xyz_min).flatten().tolist())
+        n = xyzs_w.shape[0]
+        dirs = self.__dict__.get('_unit_dirs')
+        if dirs is None or dirs.shape[0] < n or dirs.device != xyzs_w.device:
+            dirs = torch.zeros(n, 3, device=xyzs_w.device, dtype=torch.float32)
+            dirs[:, 2] = 1.0                       # the sigma head does not depend on the direction
+            self.__dict__['_unit_dirs'] = dirs
+        emb = ops.hash_encode_fwd(xyzs_w, table, enc._clayout, enc.out_dim, aabb=aabb)
+        sigmas, _ = ops.mlp_fwd(emb, dirs[:n], [w.detach() for w in mlp_weights(self)])
+        return sigmas
+
+    grid_seed = 0x6E6770      # Philox key of the occupancy-grid sampler: equal on every rank by construction
+
+    @torch.no_grad()
+    def update_density_grid_reference(self, density_threshold, warmup=False, decay=0.95, erode=False):
+        """The reference's own op sequence (networks.py:255-290 with torch.randint / nonzero), kept for comparison
+        in tests and benchmarks; not used by the training loop."""
         tmp = torch.zeros_like(self.density_grid)
         if warmup:
             cells = self.get_all_cells()
@@ -204,8 +258,6 @@ class NGP(nn.Module):
             decay = torch.clamp(decay ** (1 / self.count_grid), 0.1, 0.95)
         self.density_grid = torch.where(self.density_grid < 0, self.density_grid,
                                         torch.maximum(self.density_grid * decay, tmp))
-        # mean over the positive cells, kept on the device: the reference's `.mean().item()` (:286) is a
-        # host sync every 16th step; the threshold min(mean, density_threshold) is applied inside the kernel
         positive = self.density_grid > 0
         mean_density = (self.density_grid * positive).sum() / positive.sum()
         from taichi_nerfs_b200 import ops

@@ -358,3 +358,81 @@ def raymarching_lanes(rays_o, rays_d, hits_t, bitfield, noise, scale, grid_size,
     _chk(lib().ngp_raymarching_lanes_cpu(_p(o), _p(d), _p(h), _p(bf), _p(nz), C.c_int(grid_size), C.c_float(scale),
                                          C.c_int(max_samples), _p(ra), _p(ts), _p(counts), _p(stats), C.c_int64(n)))
     return ts, counts, {"regular_chunks": int(stats[0]), "general_chunks": int(stats[1])}
+
+
+# ---- fused occupancy-grid update (restates modules/networks.py:168-209, 255-290 with the Philox draws of grid.cu) ---
+def philox4x32_10_np(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10 (same rounds as ngp_philox4x32_10_cpu, pinned on the Random123 vectors by
+    tests/test_oracle.py).  Inputs broadcastable uint32 arrays; returns 4 uint32 arrays."""
+    c0, c1, c2, c3 = (np.asarray(v, dtype=np.uint64) for v in np.broadcast_arrays(c0, c1, c2, c3))
+    k0 = np.uint64(k0)
+    k1 = np.uint64(k1)
+    M = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & M, p1 >> np.uint64(32), p1 & M
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & M, lo1, (hi0 ^ c3 ^ k1) & M, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M
+        k1 = (k1 + np.uint64(0xBB67AE85)) & M
+    return tuple(v.astype(np.uint32) for v in (c0, c1, c2, c3))
+
+
+def grid_sample_cells(density_grid, scale, density_threshold, warmup, M, seed, step):
+    """(cell_idx [C*slots] int32, xyz [C*slots, 3] f32): get_all_cells (networks.py:168-179) in warm-up mode, else
+    sample_uniform_and_occupied_cells (:181-209) - M uniform cells then M picks among nonzero(grid > thr) in index
+    order - and the jittered positions of update_density_grid (:263-271), strict fp32."""
+    f = np.float32
+    C_, cells = density_grid.shape
+    G = round(cells ** (1 / 3))
+    slots = cells if warmup else 2 * M
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    idx_all, xyz_all = [], []
+    i = np.arange(slots, dtype=np.uint32)
+    for c in range(C_):
+        ra = philox4x32_10_np(i, np.uint32(c), np.uint32(step), np.uint32(0), k0, k1)
+        rb = philox4x32_10_np(i, np.uint32(c), np.uint32(step), np.uint32(1), k0, k1)
+        if warmup:
+            idx = i.astype(np.int64)
+        else:
+            below = lambda r, n: ((r.astype(np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int64)  # noqa: E731
+            coords1 = np.stack([below(ra[d][:M], G) for d in range(3)], -1).astype(np.int32)
+            idx1 = morton3d(coords1).astype(np.int64)
+            occ = np.nonzero(density_grid[c] > f(density_threshold))[0]
+            if len(occ) > 0:
+                idx2 = occ[below(ra[3][M:], len(occ))]
+            else:
+                idx2 = np.full(M, -1, np.int64)
+            idx = np.concatenate([idx1, idx2])
+        coords = morton3d_invert(np.maximum(idx, 0).astype(np.int32)).astype(f)
+        s = f(min(2.0 ** (c - 1), scale))
+        hg = f(s / f(G))
+        span = f(s - hg)
+        u = np.stack([(rb[d] >> np.uint32(8)).astype(f) * f(5.9604644775390625e-8) for d in range(3)], -1)
+        xyz = ((coords / f(G - 1)) * f(2) - f(1)) * span + (u * f(2) - f(1)) * hg
+        xyz[idx < 0] = 0
+        idx_all.append(idx.astype(np.int32))
+        xyz_all.append(xyz.astype(f))
+    return np.concatenate(idx_all), np.concatenate(xyz_all)
+
+
+def grid_update(density_grid, cell_idx, densities, density_threshold, decay=0.95, count_grid=None):
+    """(new grid [C, cells] f32, mean f32, bitfield u8): tmp[c, idx] = density (max over duplicates), EMA-max
+    (networks.py:276-279), mean of the positive cells (:286), packbits with min(mean, threshold) (:288-290)."""
+    f = np.float32
+    C_, cells = density_grid.shape
+    per = cell_idx.size // C_
+    tmp = np.zeros_like(density_grid)
+    for c in range(C_):
+        idx, d = cell_idx[c * per:(c + 1) * per], densities[c * per:(c + 1) * per]
+        ok = (idx >= 0) & (d >= 0)
+        np.maximum.at(tmp[c], idx[ok], d[ok].astype(f))
+    dec = f(decay)
+    if count_grid is not None:
+        dec = np.clip(np.power(f(decay), f(1) / count_grid.astype(f)).astype(f), f(0.1), f(0.95))
+    new = np.where(density_grid < 0, density_grid, np.maximum((density_grid * dec).astype(f), tmp)).astype(f)
+    pos = new > 0
+    mean = f(new[pos].astype(np.float64).sum() / pos.sum()) if pos.any() else f(np.nan)
+    thr = min(float(mean), float(density_threshold)) if pos.any() else float(density_threshold)
+    return new, mean, packbits(new.reshape(-1), thr)
+

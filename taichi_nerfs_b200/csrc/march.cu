@@ -375,14 +375,20 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
         int s0 = 0;
         if (lane == 0 && emitted > 0) s0 = atomicAdd(&counter[0], emitted);  // reserve a contiguous row range
         s0 = __shfl_sync(full, s0, 0);
+        // Capacity overflow.  Rows are handed out in atomic order, so exactly ONE ray can straddle the end of the
+        // buffers (s0 < capacity < s0 + emitted); every ray reserving after it starts beyond the capacity.  The
+        // straddling ray keeps the samples that fit (it is rendered truncated), the later ones own no rows — so every
+        // row below min(counter[0], capacity) is written by its owner and no stale row reaches the network kernels.
         const bool fits = (int64_t)s0 + emitted <= capacity;
+        const int keep = fits ? emitted : (int)max((int64_t)0, min((int64_t)emitted, capacity - (int64_t)s0));
         if (lane == 0) {
             rays_a[r * 3 + 0] = (int32_t)r;
-            rays_a[r * 3 + 1] = fits ? s0 : 0;
-            rays_a[r * 3 + 2] = fits ? emitted : 0;
-            if (!fits) atomicAdd(&counter[1], 1);  // number of rays dropped for lack of capacity
+            rays_a[r * 3 + 1] = keep > 0 ? s0 : 0;
+            rays_a[r * 3 + 2] = keep;
+            if (!fits) atomicAdd(&counter[1], 1);  // number of rays truncated / dropped for lack of capacity
         }
-        if (!fits) return;
+        if (keep == 0) return;
+        emitted = keep;
         __syncwarp();
         for (int k = lane; k < emitted; k += 32) {
             const float tt = my_buf[k];

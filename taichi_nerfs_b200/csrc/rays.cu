@@ -7,30 +7,9 @@
 // caller (the reference's own `img_idxs` / `pix_idxs`) or from Philox4x32-10 keyed by
 // (seed, step, ray) so that the launch is CUDA-graph replayable: `step` is read from device memory.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
-
-struct Philox4 {
-    uint32_t v[4];
-};
-
-// Philox4x32-10 (Salmon et al., SC'11), counter = (c0,c1,c2,c3), key = (k0,k1)
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                                uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0;
-        c1 = lo1;
-        c2 = n2;
-        c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return Philox4{{c0, c1, c2, c3}};
-}
 
 __global__ void sample_ray_batch_kernel(const float* __restrict__ image_bank, int channels,
                                         const float* __restrict__ poses, const float* __restrict__ directions,

@@ -209,6 +209,38 @@ def packbits(density_grid, threshold, bitfield, mean_dev=None):
                                       bitfield.shape[0], _stream()), "packbits_dev")
 
 
+# ---- f1: fused occupancy-grid update ------------------------------------------------------------------
+def grid_workspace(cascades, grid_size, device):
+    n = int(load().ngp_grid_workspace_bytes(int(cascades), int(grid_size)))
+    return torch.empty(n, device=device, dtype=torch.uint8)
+
+
+def grid_sample_cells(density_grid, scale, density_threshold, warmup, M, seed, step, workspace):
+    """Cells to evaluate + their jittered world positions (networks.py:168-209, 263-271) -> (cell_idx [C*slots] i32,
+    xyz [C*slots, 3] f32); slots = grid_size^3 (warm-up) or 2*M."""
+    _need_cuda(density_grid, workspace)
+    cascades, cells = density_grid.shape
+    G = round(cells ** (1 / 3))
+    slots = cells if warmup else 2 * int(M)
+    cell_idx = torch.empty(cascades * slots, device=density_grid.device, dtype=torch.int32)
+    xyz = torch.empty(cascades * slots, 3, device=density_grid.device, dtype=torch.float32)
+    check(load().ngp_grid_sample_cells(_ptr(density_grid), cascades, G, float(scale), float(density_threshold),
+                                       0 if warmup else 1, int(M), int(seed), int(step) & 0xFFFFFFFF, _ptr(workspace),
+                                       _ptr(cell_idx), _ptr(xyz), _stream()), "grid_sample_cells")
+    return cell_idx, xyz
+
+
+def grid_update(density_grid, cell_idx, densities, density_threshold, decay, workspace, mean_out, bitfield,
+                count_grid=None):
+    """Scatter-max + EMA-max + mean of the positive cells + packbits (networks.py:272-290), in place, no host sync."""
+    _need_cuda(density_grid, cell_idx, densities, workspace, mean_out, bitfield)
+    cascades, cells = density_grid.shape
+    G = round(cells ** (1 / 3))
+    check(load().ngp_grid_update(_ptr(density_grid), _ptr(cell_idx), _ptr(densities), cell_idx.numel() // cascades,
+                                 cascades, G, _ptr(count_grid), float(decay), float(density_threshold), _ptr(workspace),
+                                 _ptr(mean_out), _ptr(bitfield), _stream()), "grid_update")
+
+
 def sample_ray_batch(image_bank, poses, directions, n_rays, *, img_idxs=None, pix_idxs=None, fixed_img=-1, seed=0,
                      step=0, step_dev=None, with_noise=True, return_indices=False, out=None):
     """One launch for BaseDataset.__getitem__ + get_rays + the marching jitter (include/ngp_b200.h,

@@ -403,3 +403,44 @@ def test_psnr_vs_teacher():
     r = train_vs_teacher(torch.device('cuda'), steps=1500, train_views=32, test_views=2, downsample=0.25)
     assert r is not None
     assert r["psnr"] >= 25.0, r["psnr_views"]
+
+
+def test_update_density_grid_is_sync_free_and_matches_reference_statistics():
+    """NGP.update_density_grid: zero host synchronisations (torch's sync debug mode raises on any), and the same
+    occupancy statistics as the reference's op sequence (different random numbers, same distribution)."""
+    from modules.networks import NGP
+    torch.manual_seed(11)
+    thr = 0.01 * 1024 / 3 ** 0.5
+
+    def fresh():
+        torch.manual_seed(11)
+        m = NGP(scale=0.5, max_res=1024, half_opt=True).cuda()
+        with torch.no_grad():
+            m.pos_encoder.hash_table.mul_(4e4)       # a non-trivial density field
+        return m
+    a, b = fresh(), fresh()
+    a.update_density_grid(thr, warmup=True)          # first call builds the cached workspace / constants
+    b.update_density_grid_reference(thr, warmup=True)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        for _ in range(3):
+            a.update_density_grid(thr, warmup=False)
+        a.update_density_grid(thr, warmup=True)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    for _ in range(3):
+        b.update_density_grid_reference(thr, warmup=False)
+    b.update_density_grid_reference(thr, warmup=True)
+    occ_a = float(np.unpackbits(a.density_bitfield.cpu().numpy()).mean())
+    occ_b = float(np.unpackbits(b.density_bitfield.cpu().numpy()).mean())
+    assert 0.02 < occ_a < 0.98 and abs(occ_a - occ_b) < 0.02, (occ_a, occ_b)
+    ga, gb = a.density_grid.float().cpu().numpy(), b.density_grid.float().cpu().numpy()
+    assert abs(ga.mean() - gb.mean()) < 0.02 * abs(gb.mean())
+    # identical draws on every rank: two models with the same parameters and update counter get identical grids
+    c = fresh()
+    c.update_density_grid(thr, warmup=True)
+    for _ in range(3):
+        c.update_density_grid(thr, warmup=False)
+    c.update_density_grid(thr, warmup=True)
+    assert torch.equal(a.density_bitfield, c.density_bitfield) and torch.equal(a.density_grid, c.density_grid)

@@ -574,3 +574,59 @@ def test_hash_index_known_answers_cuda(ops, max_res):
     pts = np.tile(K.POINTS, (80, 1))                      # > one 512-sample CTA tile, repeated cells exercise the run reuse
     got = N(ops.hash_encode_fwd(T(pts), T(K.index_table(lay).reshape(-1)), lay.as_ctypes(), 32)).astype(np.float64)
     np.testing.assert_allclose(got, np.tile(want, (80, 1)), rtol=2e-6, atol=0.5)
+
+
+# ---- f1: fused occupancy-grid update ---------------------------------------------------------------------------
+@pytest.mark.parametrize("warmup", [True, False])
+@pytest.mark.parametrize("cascades,scale", [(1, 0.5), (3, 2.0)])
+def test_fused_grid_update_matches_oracle(ops, oracle, warmup, cascades, scale):
+    """Cell pick + jittered positions (networks.py:168-209, 263-271): bit-exact vs the oracle restatement (same Philox
+    draws); scatter-max + EMA-max + mean + packbits (:272-290): grid bit-exact, mean within 1 fp32 ulp, bitfield equal."""
+    G = 128
+    rng = np.random.default_rng(17 + cascades)
+    grid = (rng.random((cascades, G ** 3)) ** 6 * 40).astype(np.float32)        # ~10 % above the 5.91 threshold
+    grid[:, rng.integers(0, G ** 3, 20000)] = -1.0                               # cells no camera sees
+    thr, M, seed, step = 0.01 * 1024 / 3 ** 0.5, G ** 3 // 4, 0x6E6770, 7
+    ws = ops.grid_workspace(cascades, G, "cuda")
+    g_dev = T(grid)
+    idx, xyz = ops.grid_sample_cells(g_dev, scale, thr, warmup, M, seed, step, ws)
+    idx_ref, xyz_ref = oracle.grid_sample_cells(grid, scale, thr, warmup, M, seed, step)
+    np.testing.assert_array_equal(N(idx), idx_ref)
+    np.testing.assert_array_equal(N(xyz), xyz_ref)
+    if not warmup:   # the occupied half really is occupied, the uniform half covers the grid
+        per = 2 * M
+        for c in range(cascades):
+            occ = idx_ref[c * per + M:(c + 1) * per]
+            assert (grid[c, occ] > thr).all()
+    dens = (rng.random(idx_ref.size) ** 4 * 30).astype(np.float32)
+    mean = torch.zeros(1, device="cuda")
+    bits = torch.zeros(cascades * G ** 3 // 8, device="cuda", dtype=torch.uint8)
+    ops.grid_update(g_dev, idx, T(dens), thr, 0.95, ws, mean, bits)
+    new_ref, mean_ref, bits_ref = oracle.grid_update(grid, idx_ref, dens, thr)
+    np.testing.assert_array_equal(N(g_dev), new_ref)
+    assert abs(float(mean) - float(mean_ref)) <= 1.2e-7 * abs(float(mean_ref))
+    np.testing.assert_array_equal(N(bits), bits_ref)
+
+
+def test_fused_grid_update_no_occupied_cells_and_erode(ops, oracle):
+    """No cell above the threshold -> the occupied half is empty (index -1, networks.py:193) and ignored; erode uses the
+    per-cell decay clamp(decay^(1/count), 0.1, 0.95) (:274-275)."""
+    G = 128
+    rng = np.random.default_rng(5)
+    grid = (rng.random((1, G ** 3)) * 0.5).astype(np.float32)
+    thr, M = 5.9, G ** 3 // 4
+    ws = ops.grid_workspace(1, G, "cuda")
+    g_dev = T(grid)
+    idx, xyz = ops.grid_sample_cells(g_dev, 0.5, thr, False, M, 1, 0, ws)
+    idx_ref, xyz_ref = oracle.grid_sample_cells(grid, 0.5, thr, False, M, 1, 0)
+    assert (idx_ref[M:] == -1).all()
+    np.testing.assert_array_equal(N(idx), idx_ref)
+    np.testing.assert_array_equal(N(xyz), xyz_ref)
+    count = (rng.random((1, G ** 3)) * 0.9 + 0.05).astype(np.float32)
+    dens = rng.random(idx_ref.size).astype(np.float32)
+    mean = torch.zeros(1, device="cuda")
+    bits = torch.zeros(G ** 3 // 8, device="cuda", dtype=torch.uint8)
+    ops.grid_update(g_dev, idx, T(dens), thr, 0.95, ws, mean, bits, count_grid=T(count))
+    new_ref, mean_ref, bits_ref = oracle.grid_update(grid, idx_ref, dens, thr, count_grid=count)
+    np.testing.assert_allclose(N(g_dev), new_ref, rtol=2e-6)   # powf: 1-2 ulp between libm and CUDA
+    np.testing.assert_array_equal(N(bits), bits_ref)

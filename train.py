@@ -104,7 +104,8 @@ def main(prefix_args=None):
             extra_loss = lambda res: hparams.distortion_loss_w * distortion_loss(res).mean()  # noqa: E731
         if fast is not None:   # one graph replay, nothing synchronises the host
             loss = fast.step(rays_o, rays_d, data['rgb'])
-            results = {'rgb': fast.rgb, 'rm_samples': fast.counter[0], 'vr_samples': fast.counter[0]}
+            results = {'rgb': fast.rgb, 'rm_samples': fast.counter[0].clamp(max=fast.cap), 'vr_samples':
+                       fast.counter[0].clamp(max=fast.cap), 'dropped_rays': fast.counter[1]}
         else:
             loss, results = trainer.step(rays_o, rays_d, data['rgb'], exp_step_factor, extra_loss=extra_loss)
 
@@ -114,7 +115,9 @@ def main(prefix_args=None):
                 n = len(data['rgb'])
                 print(f"elapsed_time={time.time() - tic:.2f}s | step={step} | psnr={psnr_of(mse):.2f} | "
                       f"loss={float(loss):.6f} | rays={n} | rm_s={float(results['rm_samples']) / n:.1f} | "
-                      f"vr_s={float(results['vr_samples']) / n:.1f} | ")
+                      f"vr_s={float(results['vr_samples']) / n:.1f} | "
+                      + (f"rays truncated/dropped for capacity={int(results['dropped_rays'])} | "
+                         if int(results.get('dropped_rays', 0)) else ""))
 
     if rank != 0:
         return
