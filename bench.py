@@ -121,6 +121,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def n_samples(self):
+        return len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -295,8 +298,21 @@ def run_train(args, cfg_name, cfg):
     # untimed pre-warm beyond --warmup: the caching allocator must have seen the range of per-step
     # sample counts (every new size is a cudaMalloc) and the clocks must have ramped up
     step_fn = (lambda i, k: graph_step(i, None)) if use_graph else (lambda i, k: module_step(i, batches[k]))
-    for s in range(PREWARM):
-        step_fn(1 + s % 8, s % n_total)
+    # ... and nvidia-smi (100 ms period, slow to start on a fresh box) must have sampled the clocks UNDER THIS LOAD:
+    # keep stepping in blocks of 16 until rank 0's sampler has delivered a few samples (bounded at 4 s; the decision is
+    # shared by all ranks so that every rank runs the same number of collective steps)
+    t_pre, s = time.perf_counter(), 0
+    while True:
+        for _ in range(16):
+            step_fn(1 + s % 8, s % n_total)
+            s += 1
+        torch.cuda.synchronize()
+        more = torch.tensor([1.0 if (rank == 0 and clocks.proc is not None and clocks.n_samples() < 5
+                                     and time.perf_counter() - t_pre < 4.0) else 0.0], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(more, op=torch.distributed.ReduceOp.MAX)
+        if s >= PREWARM and float(more) == 0.0:
+            break
     for s in range(args.warmup):
         step_fn(s, s)
     launches0 = _lib.launch_count()
@@ -534,8 +550,11 @@ def run_frame(args, cfg_name, cfg):
     timed = make_timed(torch, 1, dev)
     clocks = ClockSampler(local)
     clocks.start()
-    for _ in range(max(args.warmup, 3) + 5):
+    t_pre, k = time.perf_counter(), 0
+    while k < max(args.warmup, 3) + 5 or (clocks.proc is not None and clocks.n_samples() < 5
+                                          and time.perf_counter() - t_pre < 4.0):
         res = frame(pose)
+        k += 1
     launches0 = _lib.launch_count()
     ms = timed(lambda: [frame(pose) for _ in range(args.steps)]) / args.steps
     launches = _lib.launch_count() - launches0

@@ -272,6 +272,34 @@ int ngp_distortion_bwd(const float* dL_dloss, const float* ws, const float* delt
                        const int32_t* rays_a, float* dL_dws, int64_t n_rays, int64_t n_samples,
                        void* stream);
 
+/* ---- compacting test-time renderer (north_star: persistent warps + live-ray compaction) -----------------------
+ * Replaces the host-driven loop of modules/rendering.py:96-144 (raymarching_test + boolean-mask compaction with host
+ * syncs + composite_test per iteration; the reference's device-side re-ordering: deployment/InstantNGP/taichi_ngp/
+ * kernels.py:225-260).  One frame = ngp_frame_begin, then per ROUND: ngp_frame_round_begin -> ngp_raymarching_round ->
+ * ngp_hash_encode_fwd_dyn / ngp_mlp_fwd_dyn with n_dev = state -> ngp_composite_round.  `state` (int32[8], device):
+ * [0] sample rows of the current round, [2] live rays of the current round, [3] live rays of the next round,
+ * [4] samples evaluated so far.  `alive` / `next_alive` ping-pong between rounds.  No host read is needed until the
+ * frame is complete (state[3] == 0). */
+int ngp_frame_begin(const float* hits_t, float* t_cur, int32_t* alive, int32_t* state, float* opacity, float* depth,
+                    float* rgb, int64_t n_rays, void* stream);
+int ngp_frame_round_begin(int32_t* state, void* stream);
+/* One round of marching (modules/ray_march.py:197-268 semantics: resume at t_cur[ray], strict 0 < t, no jitter):
+ * persistent warps walk alive[0 .. state[2]); every live ray emits at most min(limit, capacity / state[2]) samples
+ * (so the rows always fit), reserves them with one atomicAdd on state[0], writes rays_a[slot] = (ray, start, n) and
+ * leaves its resume point in t_cur[ray] (+inf once it has left the box). */
+int ngp_raymarching_round(const float* rays_o, const float* rays_d, const float* hits_t,
+                          const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                          float exp_step_factor, int limit, const int32_t* alive, int32_t* state, float* t_cur,
+                          int32_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts, int64_t n_rays,
+                          int64_t capacity, void* stream);
+/* composite_test (modules/volume_render_test.py:4-54) for the round's samples, accumulating into opacity/depth/rgb
+ * [n_rays], + block-level compaction of the rays that stay alive (T > T_threshold and still inside the box) into
+ * next_alive[0 .. state[3]). */
+int ngp_composite_round(const float* sigmas, const void* rgbs, int rgbs_dtype, const float* deltas, const float* ts,
+                        const int32_t* rays_a, int32_t* state, const float* t_cur, const float* hits_t,
+                        float T_threshold, float* opacity, float* depth, float* rgb, int32_t* next_alive,
+                        int64_t n_rays, void* stream);
+
 /* ---- occupancy-grid helpers ---------------------------- */
 /* replaces packbits, modules/utils.py:157-169 */
 int ngp_packbits(const float* density_grid, float density_threshold,

@@ -58,9 +58,10 @@ class HashEncoder(torch.nn.Module):
         self.register_buffer('offsets', torch.tensor(lay.offsets, dtype=torch.int32), persistent=False)
         self.register_buffer('hash_map_sizes', torch.tensor(lay.map_sizes, dtype=torch.int32), persistent=False)
 
+        import sys
         print(f'Hash Encoder: base_res={base_res} max_res={max_res} hash_level={levels} '
               f'feat_per_level={feature_per_level} per_level_scale={self.log_b} '
-              f'total_hash_size={lay.total_entries} ')
+              f'total_hash_size={lay.total_entries} ', file=sys.stderr)
 
         self.hash_table = torch.nn.Parameter(self._init_table(lay), requires_grad=True)
         self.grad_sink = None  # optional fp32 [P] buffer the backward accumulates into

@@ -60,9 +60,10 @@ class HashEncoder(torch.nn.Module):
         self.register_buffer('offsets', torch.tensor(lay.offsets, dtype=torch.int32), persistent=False)
         self.register_buffer('hash_map_sizes', torch.tensor(lay.map_sizes, dtype=torch.int32), persistent=False)
 
+        import sys
         print(f'Hash Encoder: base_res={base_res} max_res={max_res} hash_level={levels} '
               f'feat_per_level={feature_per_level} per_level_scale={self.log_b} '
-              f'total_hash_size={lay.total_entries} ')
+              f'total_hash_size={lay.total_entries} ', file=sys.stderr)
 
         # fp32 master [entries, F], U(-1e-4, 1e-4) (hash_encoder_half.py:291-299)
         table = (torch.rand(lay.total_entries, feature_per_level, dtype=torch.float32) * 2.0 - 1.0) * 1e-4

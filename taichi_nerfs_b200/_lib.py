@@ -74,6 +74,10 @@ def _declare(lib):
         "ngp_morton3d_invert": (ci, [vp, vp, i64, vp]),
         "ngp_adam_step": (ci, [vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, ci, i64, vp]),
         "ngp_check_finite": (ci, [vp, i64, vp, vp]),
+        "ngp_frame_begin": (ci, [vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+        "ngp_frame_round_begin": (ci, [vp, vp]),
+        "ngp_raymarching_round": (ci, [vp, vp, vp, vp, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
+        "ngp_composite_round": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, i64, vp]),
         "ngp_grid_workspace_bytes": (i64, [ci, ci]),
         "ngp_grid_sample_cells": (ci, [vp, ci, ci, f32, f32, ci, i64, C.c_uint64, C.c_uint32, vp, vp, vp, vp]),
         "ngp_grid_update": (ci, [vp, vp, vp, i64, ci, ci, vp, f32, f32, vp, vp, vp, vp]),

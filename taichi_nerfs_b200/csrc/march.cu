@@ -213,22 +213,28 @@ __device__ __forceinline__ float cell_exit(const MarchParams& p, const Ray& ray,
 constexpr int kRaysPerBlock = 4;
 
 // kMode: 0 = count (pass 1), 1 = write (pass 2), 2 = single pass for test-time frames (sample times are
-// buffered in shared memory, the ray reserves its rows with one atomicAdd, then writes them coalesced)
+// buffered in shared memory, the ray reserves its rows with one atomicAdd, then writes them coalesced),
+// 3 = one ROUND of the compacting test-time renderer (render.cu: persistent warps walk the list of live rays, every
+// ray resumes at t_cur[ray], emits at most `limit` samples and leaves its resume point behind)
 constexpr int kMaxFrameSamples = 1024;
+struct RoundArgs {
+    const int32_t* __restrict__ alive;      // live ray ids of this round
+    const int32_t* __restrict__ n_alive;    // their number (device)
+    float* __restrict__ t_cur;              // per ray: where the march resumes (in/out); +inf = left the box
+    int limit;                              // samples per ray this round (reduced so that all live rays fit `capacity`)
+};
+
 template <int kMode>
-__global__ void __launch_bounds__(kRaysPerBlock * 32)
-march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                        const float* __restrict__ hits_t, const float* __restrict__ noise, MarchParams p,
-                        int max_samples, int32_t* __restrict__ rays_a, int32_t* __restrict__ counter,
-                        float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
-                        float* __restrict__ ts, int64_t n, int64_t capacity) {
+__device__ __forceinline__ void march_one_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                              const float* __restrict__ hits_t, const float* __restrict__ noise,
+                                              const MarchParams& p, int max_samples, int32_t* __restrict__ rays_a,
+                                              int32_t* __restrict__ counter, float* __restrict__ xyzs,
+                                              float* __restrict__ dirs, float* __restrict__ deltas,
+                                              float* __restrict__ ts, int64_t r, int64_t slot, int64_t capacity,
+                                              float* my_buf, const RoundArgs& round) {
     constexpr bool kWrite = kMode == 1;
-    __shared__ float sbuf[kMode == 2 ? kRaysPerBlock * kMaxFrameSamples : 1];
     const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
-    if (r >= n) return;
     const unsigned full = 0xffffffffu;
-    float* my_buf = sbuf + (kMode == 2 ? (threadIdx.x >> 5) * kMaxFrameSamples : 0);
 
     int limit = max_samples;
     int64_t start = 0;
@@ -248,7 +254,11 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
     load_ray(rays_o, rays_d, r, ray);
     const float t2 = hits_t[r * 2 + 1];
     float t;
-    if (kMode == 2 && noise == nullptr) {  // test time: no jitter, strict 0 < t (ray_march.py:226)
+    float t_resume = INFINITY;   // kMode 3: where the next round continues; stays +inf when the ray leaves the box
+    if (kMode == 3) {
+        t = round.t_cur[r];
+        if (!(0.0f < t)) t = -1.0f;
+    } else if (kMode == 2 && noise == nullptr) {  // test time: no jitter, strict 0 < t (ray_march.py:226)
         t = hits_t[r * 2 + 0];
         if (!(0.0f < t)) t = -1.0f;
     } else {
@@ -362,14 +372,48 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
             ts[i] = my_t;
             deltas[i] = c.dt;
         }
-        if (kMode == 2 && ((emit >> lane) & 1u)) my_buf[emitted + __popc(emit & ((1u << lane) - 1u))] = my_t;
+        if ((kMode == 2 || kMode == 3) && ((emit >> lane) & 1u)) my_buf[emitted + __popc(emit & ((1u << lane) - 1u))] = my_t;
         emitted += __popc(emit);
+        if (kMode == 3 && emitted >= limit) {
+            // budget of this round used up: the march resumes at the position after the last emitted sample
+            // (occupied -> `t += dt`, ray_march.py:258-262), i.e. the next lane's position or the next chunk's first
+            const int q = 31 - __clz(emit);
+            const float nx = __shfl_sync(full, my_t, min(q + 1, 31));
+            t_resume = q < 31 ? nx : tk;
+            break;
+        }
         if (valid_mask != full) break;  // the ray left the box inside this chunk
         t = tk;
     }
     if (kMode == 0 && lane == 0) {
         rays_a[r * 3 + 0] = (int32_t)r;
         rays_a[r * 3 + 2] = emitted;
+    }
+    if (kMode == 3) {
+        // rows always fit: limit <= capacity / n_alive.  rays_a is indexed by the live-list slot.
+        int s0 = 0;
+        if (lane == 0 && emitted > 0) s0 = atomicAdd(&counter[0], emitted);
+        s0 = __shfl_sync(full, s0, 0);
+        if (lane == 0) {
+            rays_a[slot * 3 + 0] = (int32_t)r;
+            rays_a[slot * 3 + 1] = s0;
+            rays_a[slot * 3 + 2] = emitted;
+            round.t_cur[r] = t_resume;
+        }
+        __syncwarp();
+        for (int k = lane; k < emitted; k += 32) {
+            const float tt = my_buf[k];
+            const int64_t i = (int64_t)s0 + k;
+            xyzs[i * 3 + 0] = f_add(ray.o[0], f_mul(tt, ray.d[0]));
+            xyzs[i * 3 + 1] = f_add(ray.o[1], f_mul(tt, ray.d[1]));
+            xyzs[i * 3 + 2] = f_add(ray.o[2], f_mul(tt, ray.d[2]));
+            dirs[i * 3 + 0] = ray.d[0];
+            dirs[i * 3 + 1] = ray.d[1];
+            dirs[i * 3 + 2] = ray.d[2];
+            ts[i] = tt;
+            deltas[i] = calc_dt(tt, p.esf, p.dt_max);
+        }
+        __syncwarp();   // my_buf is reused by this warp's next ray
     }
     if (kMode == 2) {
         int s0 = 0;
@@ -403,6 +447,33 @@ march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restric
             deltas[i] = calc_dt(tt, p.esf, p.dt_max);
         }
     }
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kRaysPerBlock * 32)
+march_train_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                        const float* __restrict__ hits_t, const float* __restrict__ noise, MarchParams p,
+                        int max_samples, int32_t* __restrict__ rays_a, int32_t* __restrict__ counter,
+                        float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                        float* __restrict__ ts, int64_t n, int64_t capacity, RoundArgs round) {
+    __shared__ float sbuf[kMode >= 2 ? kRaysPerBlock * kMaxFrameSamples : 1];
+    float* my_buf = sbuf + (kMode >= 2 ? (threadIdx.x >> 5) * kMaxFrameSamples : 0);
+    if (kMode == 3) {
+        // persistent warps over the compacted list of live rays
+        const int64_t n_alive = min((int64_t)max(*round.n_alive, 0), n);
+        if (n_alive == 0) return;
+        RoundArgs ra = round;
+        ra.limit = (int)max((int64_t)1, min((int64_t)round.limit, capacity / n_alive));
+        for (int64_t slot = (int64_t)blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5); slot < n_alive;
+             slot += (int64_t)gridDim.x * kRaysPerBlock)
+            march_one_ray<3>(rays_o, rays_d, hits_t, noise, p, ra.limit, rays_a, counter, xyzs, dirs, deltas, ts,
+                             (int64_t)round.alive[slot], slot, capacity, my_buf, ra);
+        return;
+    }
+    const int64_t r = (int64_t)blockIdx.x * kRaysPerBlock + (threadIdx.x >> 5);
+    if (r >= n) return;
+    march_one_ray<kMode>(rays_o, rays_d, hits_t, noise, p, max_samples, rays_a, counter, xyzs, dirs, deltas, ts, r, r,
+                         capacity, my_buf, round);
 }
 
 // exclusive scan of rays_a[:,2] into rays_a[:,1] by one CTA; counter = (total, n_rays)
@@ -529,7 +600,7 @@ int ngp_raymarching_train_count(const float* rays_o, const float* rays_d, const 
         const unsigned grid = (unsigned)((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
         march_train_warp_kernel<0><<<grid, kRaysPerBlock * 32, 0, st>>>(
             rays_o, rays_d, hits_t, noise, p, max_samples, rays_a, counter, nullptr, nullptr, nullptr, nullptr,
-            n_rays, 0);
+            n_rays, 0, RoundArgs{});
         NGP_LAUNCHED("march_train_warp_kernel<count>");
     }
     march_scan_kernel<<<1, 1024, 0, st>>>(rays_a, counter, n_rays);
@@ -549,7 +620,7 @@ int ngp_raymarching_train_write(const float* rays_o, const float* rays_d, const 
     const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
     const unsigned grid = (unsigned)((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
     march_train_warp_kernel<1><<<grid, kRaysPerBlock * 32, 0, ngp::as_stream(stream)>>>(
-        rays_o, rays_d, hits_t, noise, p, 0, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity);
+        rays_o, rays_d, hits_t, noise, p, 0, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity, RoundArgs{});
     NGP_LAUNCHED("march_train_warp_kernel<write>");
     return 0;
 }
@@ -566,8 +637,36 @@ int ngp_raymarching_frame(const float* rays_o, const float* rays_d, const float*
     const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
     const unsigned grid = (unsigned)((n_rays + kRaysPerBlock - 1) / kRaysPerBlock);
     march_train_warp_kernel<2><<<grid, kRaysPerBlock * 32, 0, ngp::as_stream(stream)>>>(
-        rays_o, rays_d, hits_t, noise, p, max_samples, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity);
+        rays_o, rays_d, hits_t, noise, p, max_samples, rays_a, counter, xyzs, dirs, deltas, ts, n_rays, capacity,
+        RoundArgs{});
     NGP_LAUNCHED("march_train_warp_kernel<frame>");
+    return 0;
+}
+
+
+int ngp_raymarching_round(const float* rays_o, const float* rays_d, const float* hits_t,
+                          const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
+                          float exp_step_factor, int limit, const int32_t* alive, int32_t* state, float* t_cur,
+                          int32_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts, int64_t n_rays,
+                          int64_t capacity, void* stream) {
+    NGP_REQUIRE(n_rays >= 0 && capacity >= 1, "bad size");
+    if (n_rays == 0) return 0;
+    NGP_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && alive && state && t_cur && rays_a && xyzs && dirs &&
+                    deltas && ts, "null pointer");
+    NGP_REQUIRE(limit >= 1 && limit <= kMaxFrameSamples, "limit must be in [1, 1024]");
+    const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
+    RoundArgs ra;
+    ra.alive = alive;
+    ra.n_alive = state + 2;
+    ra.t_cur = t_cur;
+    ra.limit = limit;
+    // persistent warps: a few CTAs per SM walk the live list (16 KB of shared memory and 128 threads per CTA)
+    const int64_t want = (n_rays + kRaysPerBlock - 1) / kRaysPerBlock;
+    const int64_t cap_ctas = (int64_t)ngp::sm_count() * 12;
+    const unsigned grid = (unsigned)(want < cap_ctas ? want : cap_ctas);
+    march_train_warp_kernel<3><<<grid, kRaysPerBlock * 32, 0, ngp::as_stream(stream)>>>(
+        rays_o, rays_d, hits_t, nullptr, p, limit, rays_a, state, xyzs, dirs, deltas, ts, n_rays, capacity, ra);
+    NGP_LAUNCHED("march_train_warp_kernel<round>");
     return 0;
 }
 

@@ -498,6 +498,132 @@ distortion_bwd_kernel(const float* __restrict__ dL_dloss, const float* __restric
     }
 }
 
+// =====================================================================================================
+// Compacting test-time renderer (replaces the host-driven loop of modules/rendering.py:96-144 and its re-ordering
+// kernels; the reference's own device-side variant is deployment/InstantNGP/taichi_ngp/kernels.py:225-260).
+// A frame is a fixed sequence of ROUNDS; each round = [bookkeeping] -> march (csrc/march.cu, kMode 3: persistent warps
+// over the list of live rays, <= limit samples per ray, resume point kept per ray) -> hash encode -> MLP -> this
+// kernel: composite the round's samples onto the per-ray accumulators (volume_render_test.py:19-54) and COMPACT the
+// rays that are still alive (T > threshold and not out of the box) into the next round's list, one atomic per block.
+// Nothing is read back by the host between rounds: the live count and the row count stay in `state`.
+//   state[0] rows written by this round's march   state[2] live rays of this round   state[3] live rays of the next
+//   state[4] samples evaluated so far             state[1], state[5..7] spare
+constexpr int kRoundWarps = 8;
+
+__global__ void frame_begin_kernel(const float* __restrict__ hits_t, float* __restrict__ t_cur,
+                                   int32_t* __restrict__ alive, int32_t* __restrict__ state,
+                                   float* __restrict__ opacity, float* __restrict__ depth, float* __restrict__ rgb,
+                                   int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        state[0] = state[1] = 0;
+        state[2] = 0;
+        state[3] = (int32_t)n;     // becomes the live count at the first round_begin
+        state[4] = 0;
+    }
+    if (i >= n) return;
+    const float t1 = hits_t[i * 2 + 0];
+    t_cur[i] = 0.0f < t1 ? t1 : -1.0f;     // ray_march.py:226 (strict 0 < t); rays that miss the box never emit
+    alive[i] = (int32_t)i;
+    opacity[i] = 0.0f;
+    depth[i] = 0.0f;
+    rgb[i * 3 + 0] = rgb[i * 3 + 1] = rgb[i * 3 + 2] = 0.0f;
+}
+
+__global__ void frame_round_begin_kernel(int32_t* __restrict__ state) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    state[4] += state[0];
+    state[0] = 0;
+    state[2] = state[3];
+    state[3] = 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRoundWarps * 32)
+composite_round_kernel(const float* __restrict__ sigmas, const T* __restrict__ rgbs, const float* __restrict__ deltas,
+                       const float* __restrict__ ts, const int32_t* __restrict__ rays_a,
+                       int32_t* __restrict__ state, const float* __restrict__ t_cur,
+                       const float* __restrict__ hits_t, float thr, float* __restrict__ opacity,
+                       float* __restrict__ depth, float* __restrict__ rgb, int32_t* __restrict__ next_alive) {
+    __shared__ int32_t s_keep[kRoundWarps];
+    __shared__ int32_t s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_alive = state[2];
+    const int64_t n_iter = (n_alive + kRoundWarps - 1) / kRoundWarps;   // block-uniform trip count
+    for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
+        const int64_t slot = it * kRoundWarps + warp;
+        int32_t ray = -1;
+        bool keep = false;
+        if (slot < n_alive) {
+            ray = rays_a[slot * 3 + 0];
+            const int64_t start = rays_a[slot * 3 + 1];
+            const int N = rays_a[slot * 3 + 2];
+            float r = 0.f, g = 0.f, b = 0.f, dep = 0.f, op = 0.f;
+            float Tc = 1.0f - opacity[ray];     // volume_render_test.py:30
+            bool alive = true;
+            for (int base = 0; base < N && alive; base += 32) {
+                const int k = base + lane;
+                const bool valid = k < N;
+                const int64_t s = start + k;
+                float a = 0.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f, tm = 0.f;
+                if (valid) {
+                    a = 1.0f - expf(-sigmas[s] * deltas[s]);
+                    c0 = load_as_float(rgbs, s * 3 + 0);
+                    c1 = load_as_float(rgbs, s * 3 + 1);
+                    c2 = load_as_float(rgbs, s * 3 + 2);
+                    tm = ts[s];
+                }
+                const float incl = warp_scan_mul(1.0f - a, lane);
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 1.0f;
+                const float Tb = Tc * excl;               // T before this sample
+                const bool active = valid && Tb > thr;    // the loop breaks once T <= threshold (:47-49)
+                const float w = active ? a * Tb : 0.0f;
+                r += w * c0;
+                g += w * c1;
+                b += w * c2;
+                dep += w * tm;
+                op += w;
+                const unsigned act = __ballot_sync(0xffffffffu, active);
+                const unsigned val = __ballot_sync(0xffffffffu, valid);
+                if (act != val) alive = false;
+                Tc = Tc * __shfl_sync(0xffffffffu, incl, 31);
+            }
+            r = warp_sum(r);
+            g = warp_sum(g);
+            b = warp_sum(b);
+            dep = warp_sum(dep);
+            op = warp_sum(op);
+            if (lane == 0 && N > 0) {
+                rgb[ray * 3 + 0] += r;
+                rgb[ray * 3 + 1] += g;
+                rgb[ray * 3 + 2] += b;
+                depth[ray] += dep;
+                opacity[ray] += op;
+            }
+            // still alive: transmittance above the threshold and the march has not left the box (:51-52: a ray with
+            // no samples left or T <= threshold gets alive_indices = -1)
+            keep = alive && Tc > thr && t_cur[ray] < hits_t[(int64_t)ray * 2 + 1];
+        }
+        // block-level compaction of the live rays: one atomic per block
+        if (lane == 0) s_keep[warp] = keep ? 1 : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int c = 0;
+#pragma unroll
+            for (int w = 0; w < kRoundWarps; ++w) c += s_keep[w];
+            s_base = c ? atomicAdd(&state[3], c) : 0;
+        }
+        __syncthreads();
+        if (keep && lane == 0) {
+            int off = 0;
+            for (int w = 0; w < warp; ++w) off += s_keep[w];
+            next_alive[s_base + off] = ray;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -645,6 +771,47 @@ int ngp_composite_test(const float* sigmas, const void* rgbs, int rgbs_dtype, co
         composite_test_kernel<float><<<grid, 256, 0, st>>>(sigmas, (const float*)rgbs, deltas, ts, pack_info,
                                                            alive_indices, T_threshold, opacity, depth, rgb, n_alive);
     NGP_LAUNCHED("composite_test_kernel");
+    return 0;
+}
+
+int ngp_frame_begin(const float* hits_t, float* t_cur, int32_t* alive, int32_t* state, float* opacity, float* depth,
+                    float* rgb, int64_t n_rays, void* stream) {
+    NGP_REQUIRE(n_rays >= 1 && n_rays < (1ll << 31), "n_rays out of range");
+    NGP_REQUIRE(hits_t && t_cur && alive && state && opacity && depth && rgb, "null pointer");
+    frame_begin_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, ngp::as_stream(stream)>>>(hits_t, t_cur, alive, state,
+                                                                                           opacity, depth, rgb, n_rays);
+    NGP_LAUNCHED("frame_begin_kernel");
+    return 0;
+}
+
+int ngp_frame_round_begin(int32_t* state, void* stream) {
+    NGP_REQUIRE(state != nullptr, "null pointer");
+    frame_round_begin_kernel<<<1, 32, 0, ngp::as_stream(stream)>>>(state);
+    NGP_LAUNCHED("frame_round_begin_kernel");
+    return 0;
+}
+
+int ngp_composite_round(const float* sigmas, const void* rgbs, int rgbs_dtype, const float* deltas, const float* ts,
+                        const int32_t* rays_a, int32_t* state, const float* t_cur, const float* hits_t,
+                        float T_threshold, float* opacity, float* depth, float* rgb, int32_t* next_alive,
+                        int64_t n_rays, void* stream) {
+    NGP_REQUIRE(rgbs_dtype == NGP_F32 || rgbs_dtype == NGP_F16, "bad dtype");
+    NGP_REQUIRE(n_rays >= 1, "n_rays out of range");
+    NGP_REQUIRE(sigmas && rgbs && deltas && ts && rays_a && state && t_cur && hits_t && opacity && depth && rgb &&
+                    next_alive, "null pointer");
+    const int64_t want = (n_rays + kRoundWarps - 1) / kRoundWarps;
+    const int64_t cap_ctas = (int64_t)ngp::sm_count() * 8;
+    const unsigned grid = (unsigned)(want < cap_ctas ? want : cap_ctas);
+    cudaStream_t st = ngp::as_stream(stream);
+    if (rgbs_dtype == NGP_F16)
+        composite_round_kernel<__half><<<grid, kRoundWarps * 32, 0, st>>>(sigmas, (const __half*)rgbs, deltas, ts, rays_a,
+                                                                         state, t_cur, hits_t, T_threshold, opacity,
+                                                                         depth, rgb, next_alive);
+    else
+        composite_round_kernel<float><<<grid, kRoundWarps * 32, 0, st>>>(sigmas, (const float*)rgbs, deltas, ts, rays_a,
+                                                                        state, t_cur, hits_t, T_threshold, opacity,
+                                                                        depth, rgb, next_alive);
+    NGP_LAUNCHED("composite_round_kernel");
     return 0;
 }
 

@@ -93,10 +93,20 @@ def test_render_frame_equals_incremental_loop(lego_bitfield):
         R._FORCE_LOOP = True
         ref = R.render(m, o, d, test_time=True)
         R._FORCE_LOOP = False
-        got = R.render(m, o, d, test_time=True)
+        R._NO_COMPACTION = True
+        allsamples = R.render(m, o, d, test_time=True)        # march everything, shade everything, composite
+        R._NO_COMPACTION = False
+        got = R.render(m, o, d, test_time=True)               # compacting rounds (one CUDA graph per frame)
+        got2 = R.render(m, o, d, test_time=True)              # replay of the cached graph
     assert float(ref['opacity'].max()) > 0.5
     for k in ('rgb', 'opacity', 'depth'):
+        assert (ref[k] - allsamples[k]).abs().max() < 2e-3, k
         assert (ref[k] - got[k]).abs().max() < 2e-3, k
+        assert torch.equal(got[k], got2[k]), k
+    # early termination: rays that hit the dense medium leave the live list, so fewer samples are shaded than marched
+    assert int(got['total_samples']) < 0.8 * int(allsamples['total_samples']), (got['total_samples'],
+                                                                                allsamples['total_samples'])
+    assert int(got['total_samples']) >= int(ref['total_samples']) * 0.5
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
