@@ -276,13 +276,25 @@ def run_train(args, cfg_name, cfg):
     timed = make_timed(torch, world, dev)
 
     if args.ncu_window > 0:
+        # the same steps the timed region starts with (state after the pre-warm = the initial state)
+        keep = [t.clone() for t in (trainer.flat_param, trainer.exp_avg, trainer.exp_avg_sq, trainer.step_dev,
+                                     trainer.hyper, trainer.scale_state, fast.sample_step)]
         for s in range(PREWARM):
             graph_step(1 + s % 8, None)
+        fast.flush()
+        for t, k in zip((trainer.flat_param, trainer.exp_avg, trainer.exp_avg_sq, trainer.step_dev, trainer.hyper,
+                         trainer.scale_state, fast.sample_step), keep):
+            t.copy_(k)
+        if trainer._shadow_full is not None:
+            trainer._shadow_full.copy_(trainer.flat_param)
+        trainer.flat_grad.zero_()
+        for s in range(args.warmup):
+            graph_step(1 + s, None)
         fast.flush()
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         for s in range(args.ncu_window):
-            graph_step(1 + s, None)
+            graph_step(args.warmup + 1 + s, None)
         fast.flush()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
@@ -295,6 +307,32 @@ def run_train(args, cfg_name, cfg):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    # The pre-warm below runs a clock-dependent number of steps.  The timed workload must not depend on it (every
+    # step trains the model, which changes the next occupancy grid and with it the samples per ray), so the complete
+    # training state is put back afterwards: the timed region always starts from "random init + one grid update".
+    snap = {"param": trainer.flat_param.clone(), "m": trainer.exp_avg.clone(), "v": trainer.exp_avg_sq.clone(),
+            "step_dev": trainer.step_dev.clone(), "hyper": trainer.hyper.clone(), "scale": trainer.scale_state.clone(),
+            "shadow": None if trainer._shadow_full is None else trainer._shadow_full.clone(),
+            "grid": model.density_grid.clone(), "bits": model.density_bitfield.clone(),
+            "grid_step": model.__dict__.get("_grid_step", 0), "sample_step": fast.sample_step.clone(),
+            "step_count": trainer.step_count}
+
+    def restore_state():
+        fast.flush()
+        trainer.flat_param.copy_(snap["param"])
+        trainer.exp_avg.copy_(snap["m"])
+        trainer.exp_avg_sq.copy_(snap["v"])
+        trainer.step_dev.copy_(snap["step_dev"])
+        trainer.hyper.copy_(snap["hyper"])
+        trainer.scale_state.copy_(snap["scale"])
+        if snap["shadow"] is not None:
+            trainer._shadow_full.copy_(snap["shadow"])
+        trainer.flat_grad.zero_()
+        model.density_grid.copy_(snap["grid"])
+        model.density_bitfield.copy_(snap["bits"])
+        model.__dict__["_grid_step"] = snap["grid_step"]
+        fast.sample_step.copy_(snap["sample_step"])
+        trainer.step_count = snap["step_count"]
     # untimed pre-warm beyond --warmup: the caching allocator must have seen the range of per-step
     # sample counts (every new size is a cudaMalloc) and the clocks must have ramped up
     step_fn = (lambda i, k: graph_step(i, None)) if use_graph else (lambda i, k: module_step(i, batches[k]))
@@ -313,6 +351,7 @@ def run_train(args, cfg_name, cfg):
             torch.distributed.all_reduce(more, op=torch.distributed.ReduceOp.MAX)
         if s >= PREWARM and float(more) == 0.0:
             break
+    restore_state()
     for s in range(args.warmup):
         step_fn(s, s)
     launches0 = _lib.launch_count()

@@ -159,6 +159,12 @@ int ngp_hash_encode_fwd_dyn(const float* xyz, const void* table, const ngp_hash_
 int ngp_hash_encode_bwd_dyn(const float* xyz, const void* dout, int dout_dtype, const ngp_hash_layout* layout,
                             float* grad_table, int64_t n_max, const int32_t* n_dev, const float* aabb6,
                             void* stream);
+/* Same, restricted to the levels [level_begin, level_end): the levels own disjoint slices of grad_table, so a
+ * multi-GPU step scatters them in groups and all-reduces a finished group's slice while the next group runs
+ * (SURVEY.md §8e). */
+int ngp_hash_encode_bwd_levels(const float* xyz, const void* dout, int dout_dtype, const ngp_hash_layout* layout,
+                               float* grad_table, int64_t n_max, const int32_t* n_dev, const float* aabb6,
+                               int level_begin, int level_end, void* stream);
 int ngp_mlp_fwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
                     void* rgbs_f16, void* save, int64_t n_max, const int32_t* n_dev, void* stream);
 int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
@@ -291,7 +297,12 @@ int ngp_raymarching_round(const float* rays_o, const float* rays_d, const float*
                           const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
                           float exp_step_factor, int limit, const int32_t* alive, int32_t* state, float* t_cur,
                           int32_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts, int64_t n_rays,
-                          int64_t capacity, void* stream);
+                          int64_t capacity, const uint32_t* coarse_or_null, void* stream);
+/* Optional accelerator of the round march for one-cascade, constant-step scenes: coarse[(G/8)^3 / 32 words], bit s =
+ * the 8^3-cell super-cell with Morton index s, or one of its 26 neighbours, holds an occupied cell.  With it the march
+ * leaps over 256 candidate positions at a time where the ray crosses empty space; the emitted samples are unchanged
+ * (bit-exact: the leap is taken only where the reference loop would visit every position and emit nothing). */
+int ngp_build_coarse_occupancy(const uint8_t* density_bitfield, int grid_size, uint32_t* coarse, void* stream);
 /* composite_test (modules/volume_render_test.py:4-54) for the round's samples, accumulating into opacity/depth/rgb
  * [n_rays], + block-level compaction of the rays that stay alive (T > T_threshold and still inside the box) into
  * next_alive[0 .. state[3]). */

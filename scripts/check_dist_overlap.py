@@ -1,0 +1,69 @@
+"""torchrun check (N >= 2 GPUs): the graph step with per-slice all-reduces behind the backward kernels applies the
+same updates as the step with one monolithic all-reduce, parameters and occupancy grids stay identical on all ranks.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 scripts/check_dist_overlap.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from modules.networks import NGP  # noqa: E402
+from oracle.train_step import make_rays  # noqa: E402   (ray generator only)
+from taichi_nerfs_b200.fast_step import StaticTrainStep  # noqa: E402
+from taichi_nerfs_b200.trainer import NGPTrainer  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+bits = np.load(os.path.join(ROOT, "tests", "golden", "lego_bitfield.npz"))["bitfield"]
+thr = 0.01 * 1024 / 3 ** 0.5
+
+
+def run(overlap_ar, overlap_opt):
+    torch.manual_seed(3)
+    m = NGP(scale=0.5, max_res=1024, half_opt=True).cuda()
+    with torch.no_grad():
+        m.pos_encoder.hash_table.mul_(2e3)
+        m.density_bitfield.copy_(torch.from_numpy(bits))
+    tr = NGPTrainer(m, lr=1e-2)
+    fs = StaticTrainStep(tr, 4096, samples_per_ray_capacity=64, overlap_allreduce=overlap_ar, overlap_optimizer=overlap_opt)
+    losses = []
+    for k in range(4):
+        o, d = make_rays(4096, seed=100 * rank + k)          # every rank renders its own shard
+        g = torch.Generator(device="cuda").manual_seed(100 * rank + k)
+        losses.append(float(fs.step(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(),
+                                    torch.rand(4096, 3, device="cuda", generator=g),
+                                    torch.rand(4096, device="cuda", generator=g))))
+        if k == 1:
+            fs.flush()
+            m.update_density_grid(thr, warmup=False)
+    fs.flush()
+    torch.cuda.synchronize()
+    return m, tr, losses
+
+
+m1, t1, l1 = run(False, False)
+m2, t2, l2 = run(True, False)
+m3, t3, l3 = run(True, True)
+for name, (ma, mb) in {"slice all-reduce vs monolithic": (m1, m2), "+ optimizer overlap": (m1, m3)}.items():
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        bad = float(((pa - pb).abs() > 2e-3).float().mean())
+        assert bad < 2e-3, (name, bad)
+# replicas agree bit for bit: parameters and occupancy grids
+for m in (m1, m2, m3):
+    flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(flat, ref), "parameters differ across ranks"
+    g = m.density_bitfield.clone()
+    gr = g.clone()
+    dist.broadcast(gr, 0)
+    assert torch.equal(g, gr), "occupancy bitfields differ across ranks"
+if rank == 0:
+    print(f"dist overlap check ok on {world} GPUs: losses {l1} / {l2} / {l3}")
+dist.destroy_process_group()

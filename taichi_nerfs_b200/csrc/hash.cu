@@ -259,7 +259,9 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
                                                             const T* __restrict__ dout,
                                                             const __grid_constant__ ngp_hash_layout lay,
                                                             float* __restrict__ grad_table, int64_t n_max,
-                                                            const Dyn dyn) {
+                                                            const Dyn dyn, int level_begin, int level_end) {
+    // blockDim.x = 32 * (level_end - level_begin): warp w scatters level level_begin + w (the multi-GPU step launches
+    // the levels in groups so that a finished group's table slice is all-reduced while the next group runs)
     using V2 = typename Vec2<T>::type;
     const int64_t n = effective_n(dyn, n_max);
     constexpr bool kHalf = sizeof(T) == 2;
@@ -268,10 +270,11 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
     V2* tile = reinterpret_cast<V2*>(smem_raw + kXWords * sizeof(float));
 
     const int L = lay.n_levels;
+    const int nthreads = blockDim.x;
     const int64_t base = (int64_t)blockIdx.x * kTile;
     if (base >= n) return;
     const int rows = (int)min((int64_t)kTile, n - base);
-    for (int r = threadIdx.x; r < rows; r += kThreads) {
+    for (int r = threadIdx.x; r < rows; r += nthreads) {
         float v[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
     constexpr int kVec = 16 / sizeof(V2);
     if (L % kVec == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0) {
         const int groups = L / kVec;
-        for (int k = threadIdx.x; k < rows * groups; k += kThreads) {
+        for (int k = threadIdx.x; k < rows * groups; k += nthreads) {
             const int r = k / groups, l0 = (k - r * groups) * kVec;
             const uint4 raw = __ldg(reinterpret_cast<const uint4*>(d2 + (int64_t)r * L + l0));
             const V2* v = reinterpret_cast<const V2*>(&raw);
@@ -292,15 +295,15 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
             for (int q = 0; q < kVec; ++q) tile[(l0 + q) * kRow + r + r / kChunk] = v[q];
         }
     } else {
-        for (int k = threadIdx.x; k < rows * L; k += kThreads) {
+        for (int k = threadIdx.x; k < rows * L; k += nthreads) {
             const int r = k / L, l = k - r * L;
             tile[l * kRow + r + r / kChunk] = d2[k];
         }
     }
     __syncthreads();
 
-    const int level = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (level >= L) return;
+    const int level = level_begin + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (level >= L || level >= level_end) return;
     const LevelMeta m = level_meta(lay, level);
     float2* g2 = reinterpret_cast<float2*>(grad_table);
     const V2* trow = tile + level * kRow + lane * (kChunk + 1);
@@ -561,8 +564,16 @@ int ngp_hash_encode_bwd(const float* xyz, const void* dout, int dout_dtype, cons
 
 int ngp_hash_encode_bwd_dyn(const float* xyz, const void* dout, int dout_dtype, const ngp_hash_layout* layout,
                             float* grad_table, int64_t n, const int32_t* n_dev, const float* aabb6, void* stream) {
+    return ngp_hash_encode_bwd_levels(xyz, dout, dout_dtype, layout, grad_table, n, n_dev, aabb6, 0,
+                                      layout ? layout->n_levels : 0, stream);
+}
+
+int ngp_hash_encode_bwd_levels(const float* xyz, const void* dout, int dout_dtype, const ngp_hash_layout* layout,
+                               float* grad_table, int64_t n, const int32_t* n_dev, const float* aabb6, int level_begin,
+                               int level_end, void* stream) {
     const Dyn dyn = make_dyn(n_dev, aabb6);
     if (int rc = check_layout(layout)) return rc;
+    NGP_REQUIRE(level_begin >= 0 && level_begin < level_end && level_end <= layout->n_levels, "bad level range");
     NGP_REQUIRE(n >= 0, "negative n");
     NGP_REQUIRE(dout_dtype == NGP_F32 || dout_dtype == NGP_F16, "bad dtype");
     if (n == 0) return 0;
@@ -570,6 +581,7 @@ int ngp_hash_encode_bwd_dyn(const float* xyz, const void* dout, int dout_dtype, 
     NGP_REQUIRE((reinterpret_cast<uintptr_t>(grad_table) & 7) == 0, "grad_table must be 8-byte aligned");
     cudaStream_t st = ngp::as_stream(stream);
     if (layout->feat_dim != 2) {
+        NGP_REQUIRE(level_begin == 0 && level_end == layout->n_levels, "level groups need feature_per_level == 2");
         const unsigned gg = (unsigned)((n * layout->n_levels + 255) / 256);
         if (dout_dtype == NGP_F16)
             hash_bwd_generic_kernel<__half><<<gg, 256, 0, st>>>(xyz, (const __half*)dout, *layout, grad_table, n, dyn);
@@ -580,10 +592,11 @@ int ngp_hash_encode_bwd_dyn(const float* xyz, const void* dout, int dout_dtype, 
     }
     const unsigned grid = (unsigned)((n + kTile - 1) / kTile);
     if (int rc = configure_smem()) return rc;
+    const unsigned threads = 32u * (unsigned)(level_end - level_begin);
     if (dout_dtype == NGP_F16)
-        hash_bwd_kernel<__half><<<grid, kThreads, smem_bytes(layout->n_levels, 4), st>>>(xyz, (const __half*)dout, *layout, grad_table, n, dyn);
+        hash_bwd_kernel<__half><<<grid, threads, smem_bytes(layout->n_levels, 4), st>>>(xyz, (const __half*)dout, *layout, grad_table, n, dyn, level_begin, level_end);
     else
-        hash_bwd_kernel<float><<<grid, kThreads, smem_bytes(layout->n_levels, 8), st>>>(xyz, (const float*)dout, *layout, grad_table, n, dyn);
+        hash_bwd_kernel<float><<<grid, threads, smem_bytes(layout->n_levels, 8), st>>>(xyz, (const float*)dout, *layout, grad_table, n, dyn, level_begin, level_end);
     NGP_LAUNCHED("hash_bwd_kernel");
     return 0;
 }

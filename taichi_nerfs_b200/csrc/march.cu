@@ -59,6 +59,7 @@ struct MarchParams {
     float scale;
     float esf;
     float dt_max;    // SQRT3_2*scale/grid_size
+    const uint32_t* __restrict__ coarse;  // optional: dilated 8^3-cell occupancy (ngp_build_coarse_occupancy), 1 cascade
 };
 
 __device__ __forceinline__ void load_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -269,7 +270,47 @@ __device__ __forceinline__ void march_one_ray(const float* __restrict__ rays_o, 
     const bool const_dt = p.esf == 0.0f;
     const float dt0 = calc_dt(t, p.esf, p.dt_max);
 
+    // Empty-space leap (constant step, one cascade, coarse occupancy available): 256 candidate positions at once.
+    // Lane k looks at position 8k; if the DILATED super-cell (8^3 cells + its 26 neighbours) of every one of them is
+    // empty, all 256 positions lie in empty cells (consecutive test points are < 8 cells apart per axis), and if the
+    // first position is "regular" (an axis with d < -1e-3 and an unclamped coordinate, which only decreases along the
+    // ray) the reference loop visits every one of them, emits nothing and advances by exactly one step each
+    // (tests/test_oracle.py, exit quirk): t jumps to position 256 with the closed form of the fp32 recurrence.
+    bool leap_ok = false;
+    float mb0 = 0.0f, mb0_inv = 0.0f;
+    if (kMode >= 2 && p.coarse != nullptr && const_dt && p.cascades == 1) {
+        mb0 = fminf(__uint_as_float((uint32_t)(127 - 1) << 23), p.scale);
+        mb0_inv = f_div(1.0f, mb0);
+        const float dmax = fmaxf(fmaxf(fabsf(ray.d[0]), fabsf(ray.d[1])), fabsf(ray.d[2]));
+        leap_ok = dt0 * dmax * p.gsf * 0.5f * mb0_inv <= 1.0f;   // at most one cell per step and axis
+    }
+
     while (0.0f <= t && t < t2 && emitted < limit) {  // ray_march.py:43 / :86 (warp-uniform)
+        if (leap_ok && skip_until == -INFINITY) {
+            const uint32_t b = __float_as_uint(t), e = b >> 23, m = (b & 0x7fffffu) | 0x800000u;
+            const uint32_t b1 = __float_as_uint(f_add(t, dt0));
+            const uint32_t cs = ((b1 & 0x7fffffu) | 0x800000u) - m;
+            if ((b1 >> 23) == e && m + 256u * cs <= 0xffffffu &&
+                __uint_as_float((e << 23) | ((m + 255u * cs) & 0x7fffffu)) < t2) {
+                const float tq = __uint_as_float((e << 23) | ((m + (uint32_t)(8 * lane) * cs) & 0x7fffffu));
+                bool reg = false;
+                uint32_t u[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float x = f_add(ray.o[k], f_mul(tq, ray.d[k]));
+                    const float raw = f_mul(f_mul(0.5f, f_add(f_mul(x, mb0_inv), 1.0f)), p.gsf);
+                    reg = reg || (ray.d[k] < -1e-3f && raw < f_sub(p.gsf, 1.0f));
+                    u[k] = __float2uint_rz(fminf(fmaxf(raw, 0.0f), f_sub(p.gsf, 1.0f)));
+                }
+                const uint32_t sc = morton3d(u[0], u[1], u[2]) >> 9;   // Morton index of the 8^3 super-cell
+                const bool empty = ((__ldg(p.coarse + (sc >> 5)) >> (sc & 31u)) & 1u) == 0u;
+                const bool reg0 = __shfl_sync(full, reg, 0);
+                if (reg0 && __all_sync(full, empty)) {
+                    t = __uint_as_float((e << 23) | ((m + 256u * cs) & 0x7fffffu));
+                    continue;
+                }
+            }
+        }
         // t chain: position k of this chunk, identical on every lane
         float tk = t, my_t = t, my_dt = dt0;
         if (const_dt) {
@@ -554,6 +595,52 @@ __global__ void __launch_bounds__(128) march_test_kernel(const float* __restrict
     samples_counter[n] = s;
 }
 
+// dilated coarse occupancy of cascade 0: bit s (Morton index of an 8^3-cell super-cell) is set when the super-cell or
+// any of its 26 neighbours holds an occupied cell.  The bitfield is Morton ordered, so a super-cell is 512 consecutive
+// bits = 64 bytes.  One CTA, (G/8)^3 <= 4096 super-cells.
+__global__ void __launch_bounds__(1024) coarse_occupancy_kernel(const uint8_t* __restrict__ bits, int G,
+                                                                uint32_t* __restrict__ coarse) {
+    __shared__ uint8_t raw[4096];
+    const int S = G >> 3, n_sc = S * S * S;
+    for (int sc = threadIdx.x; sc < n_sc; sc += blockDim.x) {
+        const uint4* p = reinterpret_cast<const uint4*>(bits + (size_t)sc * 64);
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 v = __ldg(p + k);
+            any |= v.x | v.y | v.z | v.w;
+        }
+        raw[sc] = any ? 1 : 0;
+    }
+    __syncthreads();
+    for (int base = 0; base < n_sc; base += blockDim.x) {
+        const int sc = base + threadIdx.x;
+        bool occ = false;
+        if (sc < n_sc) {
+            // inverse of morton3d for 4 bits per axis
+            int c[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                uint32_t x = ((uint32_t)sc >> a) & 0x49249249u;
+                x = (x | (x >> 2)) & 0xc30c30c3u;
+                x = (x | (x >> 4)) & 0x0f00f00fu;
+                x = (x | (x >> 8)) & 0xff0000ffu;
+                x = (x | (x >> 16)) & 0x0000ffffu;
+                c[a] = (int)x;
+            }
+            for (int dz = -1; dz <= 1; ++dz)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
+                        if (x < 0 || y < 0 || z < 0 || x >= S || y >= S || z >= S) continue;
+                        occ = occ || raw[morton3d((uint32_t)x, (uint32_t)y, (uint32_t)z)] != 0;
+                    }
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, occ);
+        if ((threadIdx.x & 31) == 0 && sc < n_sc) coarse[sc >> 5] = word;
+    }
+}
+
 MarchParams make_params(const uint8_t* bits, int cascades, int grid_size, float scale, float esf) {
     MarchParams p;
     p.bits = bits;
@@ -567,6 +654,7 @@ MarchParams make_params(const uint8_t* bits, int cascades, int grid_size, float 
     // SQRT3_2 * scale / grid_size in fp32, mul then div (utils.py:56-57); host IEEE fp32
     volatile float m = kSqrt3x2 * scale;
     p.dt_max = m / p.gsf;
+    p.coarse = nullptr;
     return p;
 }
 
@@ -644,17 +732,28 @@ int ngp_raymarching_frame(const float* rays_o, const float* rays_d, const float*
 }
 
 
+int ngp_build_coarse_occupancy(const uint8_t* density_bitfield, int grid_size, uint32_t* coarse, void* stream) {
+    NGP_REQUIRE(density_bitfield && coarse, "null pointer");
+    NGP_REQUIRE(grid_size >= 32 && grid_size <= 128 && (grid_size & (grid_size - 1)) == 0,
+                "grid_size must be 32, 64 or 128");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(density_bitfield) & 15) == 0, "bitfield must be 16-byte aligned");
+    coarse_occupancy_kernel<<<1, 1024, 0, ngp::as_stream(stream)>>>(density_bitfield, grid_size, coarse);
+    NGP_LAUNCHED("coarse_occupancy_kernel");
+    return 0;
+}
+
 int ngp_raymarching_round(const float* rays_o, const float* rays_d, const float* hits_t,
                           const uint8_t* density_bitfield, int cascades, int grid_size, float scale,
                           float exp_step_factor, int limit, const int32_t* alive, int32_t* state, float* t_cur,
                           int32_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts, int64_t n_rays,
-                          int64_t capacity, void* stream) {
+                          int64_t capacity, const uint32_t* coarse_or_null, void* stream) {
     NGP_REQUIRE(n_rays >= 0 && capacity >= 1, "bad size");
     if (n_rays == 0) return 0;
     NGP_REQUIRE(rays_o && rays_d && hits_t && density_bitfield && alive && state && t_cur && rays_a && xyzs && dirs &&
                     deltas && ts, "null pointer");
     NGP_REQUIRE(limit >= 1 && limit <= kMaxFrameSamples, "limit must be in [1, 1024]");
-    const MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
+    MarchParams p = make_params(density_bitfield, cascades, grid_size, scale, exp_step_factor);
+    if (cascades == 1 && grid_size <= 128 && grid_size >= 32) p.coarse = coarse_or_null;
     RoundArgs ra;
     ra.alive = alive;
     ra.n_alive = state + 2;

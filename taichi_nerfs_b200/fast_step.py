@@ -31,7 +31,7 @@ def _p(t):
 class StaticTrainStep:
     def __init__(self, trainer, n_rays: int, samples_per_ray_capacity: int = 384, exp_step_factor: float = 0.0,
                  T_threshold: float = 1e-4, max_samples: int = 1024, use_graph: bool = True,
-                 dynamic_loss_scale: bool = True, overlap_optimizer: bool = False):
+                 dynamic_loss_scale: bool = True, overlap_optimizer: bool = False, overlap_allreduce=None):
         self.tr = trainer
         m = self.model = trainer.model
         enc = m.pos_encoder
@@ -90,6 +90,10 @@ class StaticTrainStep:
         self.overlap = bool(overlap_optimizer)
         self.pending = False             # gradients of the last step not applied yet (overlap mode only)
         self._side = torch.cuda.Stream(device=dev, priority=-1)
+        self._ar_stream = torch.cuda.Stream(device=dev)
+        # several ranks: all-reduce gradient slices behind the backward kernels that complete them (stock F = 2 layout)
+        self.overlap_allreduce = bool(overlap_allreduce if overlap_allreduce is not None
+                                      else (trainer.world_size > 1 and enc._clayout.feat_dim == 2))
         self.use_graph = bool(use_graph)
         if self.use_graph:
             try:
@@ -168,18 +172,62 @@ class StaticTrainStep:
         check(L.ngp_mlp_bwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.mlp_save), _p(self.dsig),
                                 _p(self.drgbs), _p(self.demb), _p(gw), self.cap, _p(self.counter), st))
 
-    def _k_hash_bwd(self):
+    def _k_hash_bwd(self, level_begin=0, level_end=None):
         L, st, tag = load(), self._st(), (F16 if self.half else F32)
-        check(L.ngp_hash_encode_bwd_dyn(_p(self.xyzs), _p(self.demb), tag, C.byref(self._clayout),
-                                        _p(self.tr.flat_grad), self.cap, _p(self.counter), self.aabb6, st))
+        level_end = self._clayout.n_levels if level_end is None else level_end
+        check(L.ngp_hash_encode_bwd_levels(_p(self.xyzs), _p(self.demb), tag, C.byref(self._clayout),
+                                           _p(self.tr.flat_grad), self.cap, _p(self.counter), self.aabb6,
+                                           int(level_begin), int(level_end), st))
+
+    def _level_groups(self):
+        """Level groups of the multi-GPU backward, most expensive first: the hashed fine levels (all-distinct cells,
+        most atomics), the hashed coarse levels, the dense levels.  Each group owns a contiguous slice of the flat
+        gradient buffer (levels are laid out in order)."""
+        lay = self._clayout
+        L_, first_hashed = lay.n_levels, lay.begin_fast_hash_level
+        mid = first_hashed + (L_ - first_hashed) // 2
+        groups = [(mid, L_), (first_hashed, mid), (0, first_hashed)]
+        return [(a, b) for a, b in groups if b > a]
+
+    def _slice_of_levels(self, a, b):
+        lay, F = self._clayout, self._clayout.feat_dim
+        lo = lay.offsets[a] * F
+        hi = (lay.offsets[b] if b < lay.n_levels else self.P // F) * F
+        return lo, hi
+
+    def _enqueue_backward_overlapped(self):
+        """Multi-GPU backward: gradient slices are all-reduced on a side stream as soon as they are complete — the MLP
+        gradients while the hash scatter runs, each level group while the next group runs — so only the last (small,
+        dense-level) slice's all-reduce is exposed."""
+        import torch.distributed as dist
+        tr, main, ar = self.tr, torch.cuda.current_stream(), self._ar_stream
+        fg = tr.flat_grad
+        reduce = tr.world_size > 1     # (a single rank can still run the grouped launches: tests)
+
+        def allreduce_behind(lo, hi):
+            ar.wait_stream(main)
+            with torch.cuda.stream(ar):
+                dist.all_reduce(fg[lo:hi], group=tr.pg)
+        self._k_mlp_bwd()
+        if reduce:
+            allreduce_behind(self.P, fg.numel())                        # MLP weight gradients (37.6 KB)
+        for a, b in self._level_groups():
+            self._k_hash_bwd(a, b)
+            if reduce:
+                allreduce_behind(*self._slice_of_levels(a, b))
+        if reduce:
+            main.wait_stream(ar)
 
     def _enqueue_network(self):
         # counter[0] = number of valid sample rows, read on the device by every kernel
         self._k_hash_fwd()
         self._k_mlp_fwd()
         self._k_head()
-        self._k_mlp_bwd()
-        self._k_hash_bwd()
+        if self.overlap_allreduce:
+            self._enqueue_backward_overlapped()
+        else:
+            self._k_mlp_bwd()
+            self._k_hash_bwd()
 
     def _enqueue_sampler(self):
         """datasets/base.py:34-61 + ray_utils.py:51-80 + the marching jitter, keyed by (seed, batch counter, ray)."""
@@ -190,7 +238,9 @@ class StaticTrainStep:
                                           _p(self.gt), _p(self.noise), None, None, self.n, self._st()))
 
     def _enqueue_update(self):
-        self.tr.enqueue_update()   # [all-reduce] -> check_finite -> LR/bias scalars -> fused Adam -> GradScaler.update
+        # [all-reduce, unless the backward already reduced slice by slice] -> check_finite -> LR/bias scalars ->
+        # fused Adam -> GradScaler.update
+        self.tr.enqueue_update(allreduce=not self.overlap_allreduce)
 
     def _enqueue(self, sampled=False, mode="sync"):
         if sampled:

@@ -115,7 +115,8 @@ class FrameRenderer:
     """
     SCHEDULE = (4, 8, 16, 32, 64, 128, 256, 512, 4)     # samples per live ray and round; sums to max_samples = 1024
 
-    def __init__(self, model, n_rays, exp_step_factor=0.0, T_threshold=1e-4, rows_per_ray=6, use_graph=True):
+    def __init__(self, model, n_rays, exp_step_factor=0.0, T_threshold=1e-4, rows_per_ray=6, use_graph=True,
+                 use_leap=True):
         import ctypes as C
         from ._lib import F16, F32, MlpWeights, check, load
         self._C, self._check, self._load = C, check, load
@@ -138,6 +139,9 @@ class FrameRenderer:
         self.xyzs, self.dirs, self.deltas, self.ts = z(cap, 3), z(cap, 3), z(cap), z(cap)
         self.emb, self.sig, self.rgbs = z(cap, 32, dtype=edt), z(cap), z(cap, 3, dtype=torch.float16)
         self.opacity, self.depth, self.rgb = z(n), z(n), z(n, 3)
+        self.coarse = None
+        if use_leap and model.cascades == 1 and model.grid_size in (32, 64, 128) and self.esf == 0.0:
+            self.coarse = z(max((model.grid_size // 8) ** 3 // 32, 1), dtype=i32)
         self.aabb6 = (C.c_float * 6)(*[float(v) for v in model.xyz_min.flatten().tolist()],
                                      *[float(v) for v in (model.xyz_max - model.xyz_min).flatten().tolist()])
         self._w_keep = [w.detach().float().contiguous() for w in mlp_weights(model)]
@@ -165,7 +169,7 @@ class FrameRenderer:
         check(L.ngp_raymarching_round(p(self.rays_o), p(self.rays_d), p(self.hits), p(m.density_bitfield), m.cascades,
                                       m.grid_size, float(m.scale), self.esf, int(limit), p(cur), p(self.state),
                                       p(self.t_cur), p(self.rays_a), p(self.xyzs), p(self.dirs), p(self.deltas),
-                                      p(self.ts), self.n, self.cap, st))
+                                      p(self.ts), self.n, self.cap, p(self.coarse), st))
         check(L.ngp_hash_encode_fwd_dyn(p(self.xyzs), p(self._table_t), self._C.byref(self._clayout), p(self.emb), self.tag,
                                         self.cap, p(self.state), self.aabb6, st))
         check(L.ngp_mlp_fwd_dyn(p(self.emb), self.tag, p(self.dirs), self._C.byref(self._wst), p(self.sig), p(self.rgbs),
@@ -179,6 +183,8 @@ class FrameRenderer:
         check(L.ngp_ray_aabb_intersect(p(self.rays_o), p(self.rays_d), float(m.scale), p(self.hits), self.n, st))
         check(L.ngp_frame_begin(p(self.hits), p(self.t_cur), p(self.alive[0]), p(self.state), p(self.opacity),
                                 p(self.depth), p(self.rgb), self.n, st))
+        if self.coarse is not None:   # 8^3-cell dilated occupancy: lets the march leap over empty space
+            check(L.ngp_build_coarse_occupancy(p(m.density_bitfield), m.grid_size, p(self.coarse), st))
         for j, limit in enumerate(self.SCHEDULE):
             self._enqueue_round(j, limit)
 

@@ -122,12 +122,13 @@ class NGPTrainer:
         (loss * scale).backward()
         return loss, results
 
-    def enqueue_update(self):
+    def enqueue_update(self, allreduce: bool = True):
         """[all-reduce] -> inf check -> LR / bias-correction scalars -> fused Adam (+fp16 shadow, grad zero) ->
         GradScaler.update(), all on the current stream with device-side scalars (graph-capturable)."""
         L, st = load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
         fg = self.flat_grad
-        parallel.allreduce_gradients(fg, self.pg)
+        if allreduce:
+            parallel.allreduce_gradients(fg, self.pg)
         check(L.ngp_check_finite(_p(fg), fg.numel(), _p(self.found_inf), st))   # after the sum: identical on every rank
         # inv_scale: static (host constant) or the device value maintained by ngp_loss_scale_update (-1 sentinel)
         inv = -1.0 if self.dynamic_loss_scale else parallel.inv_grad_scale(self.loss_scale, self.world_size)

@@ -630,3 +630,75 @@ def test_fused_grid_update_no_occupied_cells_and_erode(ops, oracle):
     new_ref, mean_ref, bits_ref = oracle.grid_update(grid, idx_ref, dens, thr, count_grid=count)
     np.testing.assert_allclose(N(g_dev), new_ref, rtol=2e-6)   # powf: 1-2 ulp between libm and CUDA
     np.testing.assert_array_equal(N(bits), bits_ref)
+
+
+# ---- compacting renderer: round march (resume points, empty-space leap) --------------------------------------------
+@pytest.mark.parametrize("leap", [False, True])
+def test_round_march_equals_full_march(ops, lego_bitfield, rays_factory, leap):
+    """The per-round march of the compacting frame renderer (persistent warps over a live list, <= limit samples per
+    ray and round, resume at t_cur, optional 256-position leap over empty space guided by the dilated coarse occupancy)
+    must emit, ray by ray, exactly the samples of the one-shot march (bit-exact t, delta, xyz), whatever the rounds."""
+    import ctypes as C
+    from taichi_nerfs_b200 import _lib
+    L = _lib.load()
+    n = 6000
+    o, d = rays_factory(n, seed=77)
+    o, d = T(o), T(d)
+    bits = T(lego_bitfield)
+    hits = ops.ray_aabb_intersect(o, d, 0.5)
+    zeros = torch.zeros(n, device="cuda")
+    counter, rays_a = ops.raymarching_train_count(o, d, hits, bits, zeros, 1, 0.5, 0.0, 128, 1024)
+    S = int(counter[0])
+    xyz_ref, dirs_ref = torch.empty(S, 3, device="cuda"), torch.empty(S, 3, device="cuda")
+    dl_ref, ts_ref = torch.empty(S, device="cuda"), torch.empty(S, device="cuda")
+    ops.raymarching_train_write(o, d, hits, bits, zeros, 1, 0.5, 0.0, 128, counter, rays_a, xyz_ref, dirs_ref, dl_ref, ts_ref)
+    ra = N(rays_a)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cap = 64 * n
+    t_cur = torch.where(hits[:, 0] > 0, hits[:, 0], torch.full_like(hits[:, 0], -1.0)).contiguous()
+    alive = torch.arange(n, device="cuda", dtype=torch.int32)
+    state = torch.zeros(8, device="cuda", dtype=torch.int32)
+    r_a = torch.zeros(n, 3, device="cuda", dtype=torch.int32)
+    xyz, dirs = torch.empty(cap, 3, device="cuda"), torch.empty(cap, 3, device="cuda")
+    dl, ts = torch.empty(cap, device="cuda"), torch.empty(cap, device="cuda")
+    coarse = None
+    if leap:
+        coarse = torch.zeros(128, device="cuda", dtype=torch.int32)
+        _lib.check(L.ngp_build_coarse_occupancy(p(bits), 128, p(coarse), st))
+        c = N(coarse).view(np.uint32)
+        occupied_sc = sum(bin(int(w)).count("1") for w in c)
+        assert 0 < occupied_sc < 4096 * 0.6, occupied_sc            # the Lego grid leaves most super-cells empty
+    got = [[] for _ in range(n)]
+    schedule = [4, 8, 16, 3, 64, 128, 256, 512]
+    rounds = 0
+    while not bool(((t_cur == float("inf")) | (t_cur < 0)).all()) and rounds < 64:
+        limit = schedule[rounds] if rounds < len(schedule) else 512
+        rounds += 1
+        state.zero_()
+        state[2] = n                                                  # every ray stays on the live list
+        _lib.check(L.ngp_raymarching_round(p(o), p(d), p(hits), p(bits), 1, 128, 0.5, 0.0, limit, p(alive), p(state),
+                                           p(t_cur), p(r_a), p(xyz), p(dirs), p(dl), p(ts), n, cap,
+                                           None if coarse is None else p(coarse), st))
+        rows = int(state[0])
+        eff = max(1, min(limit, cap // n))
+        r_np, ts_np, dl_np, xyz_np = N(r_a), N(ts)[:rows], N(dl)[:rows], N(xyz)[:rows]
+        assert (r_np[:, 2] <= eff).all() and int(r_np[:, 2].sum()) == rows
+        for ray, s0, k in r_np:
+            if k:
+                got[ray].append((ts_np[s0:s0 + k], dl_np[s0:s0 + k], xyz_np[s0:s0 + k]))
+    done = (t_cur == float("inf")) | (t_cur < 0)
+    assert bool(done.all()), "every ray must have left the box"
+    ts_r, dl_r, xyz_r = N(ts_ref), N(dl_ref), N(xyz_ref)
+    total = 0
+    for ray, s0, k in ra:
+        if k == 0:
+            assert not got[ray]
+            continue
+        t_all = np.concatenate([g[0] for g in got[ray]])
+        assert t_all.shape[0] == k, (ray, t_all.shape[0], k)
+        np.testing.assert_array_equal(t_all, ts_r[s0:s0 + k])
+        np.testing.assert_array_equal(np.concatenate([g[1] for g in got[ray]]), dl_r[s0:s0 + k])
+        np.testing.assert_array_equal(np.concatenate([g[2] for g in got[ray]]), xyz_r[s0:s0 + k])
+        total += k
+    assert total == S and S > 50000
