@@ -587,6 +587,18 @@ def run_frame(args, cfg_name, cfg):
             return render(model, rays_o, rays_d, test_time=True, exp_step_factor=cfg["esf"])   # gui.py:129-137
 
     timed = make_timed(torch, 1, dev)
+    if args.ncu_window > 0:
+        for _ in range(5):
+            frame(pose)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(args.ncu_window):
+            res = frame(pose)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_window_steps": args.ncu_window, "config": cfg_name,
+                          "samples_per_step": int(res["total_samples"])}))
+        return
     clocks = ClockSampler(local)
     clocks.start()
     t_pre, k = time.perf_counter(), 0

@@ -305,11 +305,11 @@ int ngp_raymarching_round(const float* rays_o, const float* rays_d, const float*
 int ngp_build_coarse_occupancy(const uint8_t* density_bitfield, int grid_size, uint32_t* coarse, void* stream);
 /* composite_test (modules/volume_render_test.py:4-54) for the round's samples, accumulating into opacity/depth/rgb
  * [n_rays], + block-level compaction of the rays that stay alive (T > T_threshold and still inside the box) into
- * next_alive[0 .. state[3]). */
+ * next_alive[0 .. state[3]).  `limit` = the round's sample budget per ray (picks how many lanes share a ray). */
 int ngp_composite_round(const float* sigmas, const void* rgbs, int rgbs_dtype, const float* deltas, const float* ts,
                         const int32_t* rays_a, int32_t* state, const float* t_cur, const float* hits_t,
                         float T_threshold, float* opacity, float* depth, float* rgb, int32_t* next_alive,
-                        int64_t n_rays, void* stream);
+                        int64_t n_rays, int limit, void* stream);
 
 /* ---- occupancy-grid helpers ---------------------------- */
 /* replaces packbits, modules/utils.py:157-169 */

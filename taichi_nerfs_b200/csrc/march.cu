@@ -270,12 +270,12 @@ __device__ __forceinline__ void march_one_ray(const float* __restrict__ rays_o, 
     const bool const_dt = p.esf == 0.0f;
     const float dt0 = calc_dt(t, p.esf, p.dt_max);
 
-    // Empty-space leap (constant step, one cascade, coarse occupancy available): 256 candidate positions at once.
-    // Lane k looks at position 8k; if the DILATED super-cell (8^3 cells + its 26 neighbours) of every one of them is
-    // empty, all 256 positions lie in empty cells (consecutive test points are < 8 cells apart per axis), and if the
-    // first position is "regular" (an axis with d < -1e-3 and an unclamped coordinate, which only decreases along the
-    // ray) the reference loop visits every one of them, emits nothing and advances by exactly one step each
-    // (tests/test_oracle.py, exit quirk): t jumps to position 256 with the closed form of the fp32 recurrence.
+    // Empty-space leap (constant step, one cascade, coarse occupancy available): up to 256 candidate positions at once.
+    // Lane j looks at position 8j; if the DILATED super-cell (8^3 cells + its 26 neighbours) there is empty, positions
+    // 8j .. 8j+7 lie in empty cells (they are < 8 cells away per axis).  If the first position is "regular" (an axis
+    // with d < -1e-3 and an unclamped coordinate, which only decreases along the ray) the reference loop visits every
+    // position, emits nothing in empty cells and advances by exactly one step each (tests/test_oracle.py, exit quirk),
+    // so with f leading lanes vouching t jumps to position 8f by the closed form of the fp32 recurrence.
     bool leap_ok = false;
     float mb0 = 0.0f, mb0_inv = 0.0f;
     if (kMode >= 2 && p.coarse != nullptr && const_dt && p.cascades == 1) {
@@ -284,15 +284,20 @@ __device__ __forceinline__ void march_one_ray(const float* __restrict__ rays_o, 
         const float dmax = fmaxf(fmaxf(fabsf(ray.d[0]), fabsf(ray.d[1])), fabsf(ray.d[2]));
         leap_ok = dt0 * dmax * p.gsf * 0.5f * mb0_inv <= 1.0f;   // at most one cell per step and axis
     }
+    bool try_leap = leap_ok;
 
     while (0.0f <= t && t < t2 && emitted < limit) {  // ray_march.py:43 / :86 (warp-uniform)
-        if (leap_ok && skip_until == -INFINITY) {
+        if (try_leap && skip_until == -INFINITY) {
             const uint32_t b = __float_as_uint(t), e = b >> 23, m = (b & 0x7fffffu) | 0x800000u;
             const uint32_t b1 = __float_as_uint(f_add(t, dt0));
             const uint32_t cs = ((b1 & 0x7fffffu) | 0x800000u) - m;
-            if ((b1 >> 23) == e && m + 256u * cs <= 0xffffffu &&
-                __uint_as_float((e << 23) | ((m + 255u * cs) & 0x7fffffu)) < t2) {
+            int f = 0;
+            if ((b1 >> 23) == e) {
+                // lane j vouches for positions 8j .. 8j+7 (and the landing position 8j+8): same binade as t (closed
+                // form valid), all inside the box and within 7 steps of position 8j, whose dilated super-cell is empty
+                const bool in_binade = m + (uint32_t)(8 * lane + 8) * cs <= 0xffffffu;
                 const float tq = __uint_as_float((e << 23) | ((m + (uint32_t)(8 * lane) * cs) & 0x7fffffu));
+                const float tl = __uint_as_float((e << 23) | ((m + (uint32_t)(8 * lane + 7) * cs) & 0x7fffffu));
                 bool reg = false;
                 uint32_t u[3];
 #pragma unroll
@@ -303,13 +308,16 @@ __device__ __forceinline__ void march_one_ray(const float* __restrict__ rays_o, 
                     u[k] = __float2uint_rz(fminf(fmaxf(raw, 0.0f), f_sub(p.gsf, 1.0f)));
                 }
                 const uint32_t sc = morton3d(u[0], u[1], u[2]) >> 9;   // Morton index of the 8^3 super-cell
-                const bool empty = ((__ldg(p.coarse + (sc >> 5)) >> (sc & 31u)) & 1u) == 0u;
+                const bool ok = in_binade && tl < t2 && ((__ldg(p.coarse + (sc >> 5)) >> (sc & 31u)) & 1u) == 0u;
+                const unsigned okm = __ballot_sync(full, ok);
                 const bool reg0 = __shfl_sync(full, reg, 0);
-                if (reg0 && __all_sync(full, empty)) {
-                    t = __uint_as_float((e << 23) | ((m + 256u * cs) & 0x7fffffu));
-                    continue;
-                }
+                f = reg0 ? (okm == full ? 32 : __ffs(~okm) - 1) : 0;    // leading lanes that vouch
             }
+            if (f >= 4) {   // >= 32 positions: cheaper than testing them one by one
+                t = __uint_as_float((e << 23) | ((m + (uint32_t)(8 * f) * cs) & 0x7fffffu));
+                continue;
+            }
+            try_leap = false;   // close to geometry: test positions one by one until a whole chunk comes out empty
         }
         // t chain: position k of this chunk, identical on every lane
         float tk = t, my_t = t, my_dt = dt0;
@@ -345,6 +353,7 @@ __device__ __forceinline__ void march_one_ray(const float* __restrict__ rays_o, 
         const CellTest c = test_cell(p, ray, my_t, my_dt);
         const unsigned valid_mask = __ballot_sync(full, valid);
         const unsigned occ_mask = __ballot_sync(full, valid && c.occ);
+        if (leap_ok) try_leap = occ_mask == 0u;   // a chunk without any occupied position: back in empty space
 
         // Independent-positions fast path: if every in-box lane is occupied or "regular" (and no jump is pending from
         // the previous chunk) each visited position's successor is simply the next one, so the visited set is the

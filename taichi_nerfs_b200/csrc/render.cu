@@ -538,20 +538,27 @@ __global__ void frame_round_begin_kernel(int32_t* __restrict__ state) {
     state[3] = 0;
 }
 
-template <typename T>
+// G lanes per ray (G = 4, 8, 16 or 32, >= the round's sample budget when that is small): a warp composites 32 / G rays
+// at once, so the early rounds (a handful of samples for each of ~10^5..10^6 live rays) are not latency-bound on
+// one-ray-per-warp chains.
+template <typename T, int G>
 __global__ void __launch_bounds__(kRoundWarps * 32)
 composite_round_kernel(const float* __restrict__ sigmas, const T* __restrict__ rgbs, const float* __restrict__ deltas,
                        const float* __restrict__ ts, const int32_t* __restrict__ rays_a,
                        int32_t* __restrict__ state, const float* __restrict__ t_cur,
                        const float* __restrict__ hits_t, float thr, float* __restrict__ opacity,
                        float* __restrict__ depth, float* __restrict__ rgb, int32_t* __restrict__ next_alive) {
+    constexpr int kPerWarp = 32 / G;
     __shared__ int32_t s_keep[kRoundWarps];
     __shared__ int32_t s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gi = lane / G, sub = lane % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (gi * G));
     const int64_t n_alive = state[2];
-    const int64_t n_iter = (n_alive + kRoundWarps - 1) / kRoundWarps;   // block-uniform trip count
+    const int64_t per_block = (int64_t)kRoundWarps * kPerWarp;
+    const int64_t n_iter = (n_alive + per_block - 1) / per_block;   // block-uniform trip count
     for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
-        const int64_t slot = it * kRoundWarps + warp;
+        const int64_t slot = (it * kRoundWarps + warp) * kPerWarp + gi;
         int32_t ray = -1;
         bool keep = false;
         if (slot < n_alive) {
@@ -561,8 +568,8 @@ composite_round_kernel(const float* __restrict__ sigmas, const T* __restrict__ r
             float r = 0.f, g = 0.f, b = 0.f, dep = 0.f, op = 0.f;
             float Tc = 1.0f - opacity[ray];     // volume_render_test.py:30
             bool alive = true;
-            for (int base = 0; base < N && alive; base += 32) {
-                const int k = base + lane;
+            for (int base = 0; base < N && alive; base += G) {
+                const int k = base + sub;
                 const bool valid = k < N;
                 const int64_t s = start + k;
                 float a = 0.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f, tm = 0.f;
@@ -573,9 +580,14 @@ composite_round_kernel(const float* __restrict__ sigmas, const T* __restrict__ r
                     c2 = load_as_float(rgbs, s * 3 + 2);
                     tm = ts[s];
                 }
-                const float incl = warp_scan_mul(1.0f - a, lane);
-                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                if (lane == 0) excl = 1.0f;
+                float incl = 1.0f - a;            // inclusive prefix product inside the group
+#pragma unroll
+                for (int o = 1; o < G; o <<= 1) {
+                    const float nb = __shfl_up_sync(gmask, incl, o, G);
+                    if (sub >= o) incl *= nb;
+                }
+                float excl = __shfl_up_sync(gmask, incl, 1, G);
+                if (sub == 0) excl = 1.0f;
                 const float Tb = Tc * excl;               // T before this sample
                 const bool active = valid && Tb > thr;    // the loop breaks once T <= threshold (:47-49)
                 const float w = active ? a * Tb : 0.0f;
@@ -584,17 +596,20 @@ composite_round_kernel(const float* __restrict__ sigmas, const T* __restrict__ r
                 b += w * c2;
                 dep += w * tm;
                 op += w;
-                const unsigned act = __ballot_sync(0xffffffffu, active);
-                const unsigned val = __ballot_sync(0xffffffffu, valid);
+                const unsigned act = __ballot_sync(gmask, active) & gmask;
+                const unsigned val = __ballot_sync(gmask, valid) & gmask;
                 if (act != val) alive = false;
-                Tc = Tc * __shfl_sync(0xffffffffu, incl, 31);
+                Tc = Tc * __shfl_sync(gmask, incl, G - 1, G);
             }
-            r = warp_sum(r);
-            g = warp_sum(g);
-            b = warp_sum(b);
-            dep = warp_sum(dep);
-            op = warp_sum(op);
-            if (lane == 0 && N > 0) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                r += __shfl_xor_sync(gmask, r, o, G);
+                g += __shfl_xor_sync(gmask, g, o, G);
+                b += __shfl_xor_sync(gmask, b, o, G);
+                dep += __shfl_xor_sync(gmask, dep, o, G);
+                op += __shfl_xor_sync(gmask, op, o, G);
+            }
+            if (sub == 0 && N > 0) {
                 rgb[ray * 3 + 0] += r;
                 rgb[ray * 3 + 1] += g;
                 rgb[ray * 3 + 2] += b;
@@ -606,7 +621,8 @@ composite_round_kernel(const float* __restrict__ sigmas, const T* __restrict__ r
             keep = alive && Tc > thr && t_cur[ray] < hits_t[(int64_t)ray * 2 + 1];
         }
         // block-level compaction of the live rays: one atomic per block
-        if (lane == 0) s_keep[warp] = keep ? 1 : 0;
+        const unsigned kept = __ballot_sync(0xffffffffu, keep && sub == 0);
+        if (lane == 0) s_keep[warp] = __popc(kept);
         __syncthreads();
         if (threadIdx.x == 0) {
             int c = 0;
@@ -615,8 +631,8 @@ composite_round_kernel(const float* __restrict__ sigmas, const T* __restrict__ r
             s_base = c ? atomicAdd(&state[3], c) : 0;
         }
         __syncthreads();
-        if (keep && lane == 0) {
-            int off = 0;
+        if (keep && sub == 0) {
+            int off = __popc(kept & ((1u << lane) - 1u));
             for (int w = 0; w < warp; ++w) off += s_keep[w];
             next_alive[s_base + off] = ray;
         }
@@ -794,23 +810,32 @@ int ngp_frame_round_begin(int32_t* state, void* stream) {
 int ngp_composite_round(const float* sigmas, const void* rgbs, int rgbs_dtype, const float* deltas, const float* ts,
                         const int32_t* rays_a, int32_t* state, const float* t_cur, const float* hits_t,
                         float T_threshold, float* opacity, float* depth, float* rgb, int32_t* next_alive,
-                        int64_t n_rays, void* stream) {
+                        int64_t n_rays, int limit, void* stream) {
     NGP_REQUIRE(rgbs_dtype == NGP_F32 || rgbs_dtype == NGP_F16, "bad dtype");
-    NGP_REQUIRE(n_rays >= 1, "n_rays out of range");
+    NGP_REQUIRE(n_rays >= 1 && limit >= 1, "n_rays / limit out of range");
     NGP_REQUIRE(sigmas && rgbs && deltas && ts && rays_a && state && t_cur && hits_t && opacity && depth && rgb &&
                     next_alive, "null pointer");
-    const int64_t want = (n_rays + kRoundWarps - 1) / kRoundWarps;
+    const int G = limit <= 4 ? 4 : limit <= 8 ? 8 : limit <= 16 ? 16 : 32;   // lanes per ray
+    const int64_t per_block = (int64_t)kRoundWarps * (32 / G);
+    const int64_t want = (n_rays + per_block - 1) / per_block;
     const int64_t cap_ctas = (int64_t)ngp::sm_count() * 8;
     const unsigned grid = (unsigned)(want < cap_ctas ? want : cap_ctas);
     cudaStream_t st = ngp::as_stream(stream);
-    if (rgbs_dtype == NGP_F16)
-        composite_round_kernel<__half><<<grid, kRoundWarps * 32, 0, st>>>(sigmas, (const __half*)rgbs, deltas, ts, rays_a,
-                                                                         state, t_cur, hits_t, T_threshold, opacity,
-                                                                         depth, rgb, next_alive);
-    else
-        composite_round_kernel<float><<<grid, kRoundWarps * 32, 0, st>>>(sigmas, (const float*)rgbs, deltas, ts, rays_a,
-                                                                        state, t_cur, hits_t, T_threshold, opacity,
-                                                                        depth, rgb, next_alive);
+#define NGP_CR(TT, GG)                                                                                              \
+    composite_round_kernel<TT, GG><<<grid, kRoundWarps * 32, 0, st>>>(sigmas, (const TT*)rgbs, deltas, ts, rays_a, state, \
+                                                                      t_cur, hits_t, T_threshold, opacity, depth, rgb,   \
+                                                                      next_alive)
+#define NGP_CR_G(TT)               \
+    do {                           \
+        if (G == 4) NGP_CR(TT, 4); \
+        else if (G == 8) NGP_CR(TT, 8); \
+        else if (G == 16) NGP_CR(TT, 16); \
+        else NGP_CR(TT, 32);       \
+    } while (0)
+    if (rgbs_dtype == NGP_F16) NGP_CR_G(__half);
+    else NGP_CR_G(float);
+#undef NGP_CR_G
+#undef NGP_CR
     NGP_LAUNCHED("composite_round_kernel");
     return 0;
 }

@@ -92,8 +92,9 @@ class StaticTrainStep:
         self._side = torch.cuda.Stream(device=dev, priority=-1)
         self._ar_stream = torch.cuda.Stream(device=dev)
         # several ranks: all-reduce gradient slices behind the backward kernels that complete them (stock F = 2 layout)
-        self.overlap_allreduce = bool(overlap_allreduce if overlap_allreduce is not None
-                                      else (trainer.world_size > 1 and enc._clayout.feat_dim == 2))
+        import os
+        default_ar = trainer.world_size > 1 and enc._clayout.feat_dim == 2 and os.environ.get("NGP_AR_OVERLAP", "1") != "0"
+        self.overlap_allreduce = bool(overlap_allreduce if overlap_allreduce is not None else default_ar)
         self.use_graph = bool(use_graph)
         if self.use_graph:
             try:

@@ -176,7 +176,7 @@ class FrameRenderer:
                                 None, self.cap, p(self.state), st))
         check(L.ngp_composite_round(p(self.sig), p(self.rgbs), 1, p(self.deltas), p(self.ts), p(self.rays_a),
                                     p(self.state), p(self.t_cur), p(self.hits), self.T_thr, p(self.opacity),
-                                    p(self.depth), p(self.rgb), p(nxt), self.n, st))
+                                    p(self.depth), p(self.rgb), p(nxt), self.n, int(limit), st))
 
     def _enqueue_frame(self):
         L, m, st, p, check = self._load(), self.model, self._C.c_void_p(torch.cuda.current_stream().cuda_stream), self._p, self._check
