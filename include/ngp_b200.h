@@ -161,15 +161,16 @@ int ngp_hash_encode_bwd_dyn(const float* xyz, const void* dout, int dout_dtype, 
                             void* stream);
 /* Same, restricted to the levels [level_begin, level_end): the levels own disjoint slices of grad_table, so a
  * multi-GPU step scatters them in groups and all-reduces a finished group's slice while the next group runs
- * (SURVEY.md §8e). */
+ * (SURVEY.md §8e).  found_inf_or_null: set to 1 when a non-finite contribution is scattered - GradScaler's inf check
+ * raised at the source instead of a separate pass over the gradient buffer (ngp_check_finite). */
 int ngp_hash_encode_bwd_levels(const float* xyz, const void* dout, int dout_dtype, const ngp_hash_layout* layout,
                                float* grad_table, int64_t n_max, const int32_t* n_dev, const float* aabb6,
-                               int level_begin, int level_end, void* stream);
+                               int level_begin, int level_end, int32_t* found_inf_or_null, void* stream);
 int ngp_mlp_fwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, float* sigmas,
                     void* rgbs_f16, void* save, int64_t n_max, const int32_t* n_dev, void* stream);
 int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
                     const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n_max,
-                    const int32_t* n_dev, void* stream);
+                    const int32_t* n_dev, int32_t* found_inf_or_null, void* stream);
 /* Adam with the per-step scalars in device memory: hyper_dev[4] = {lr/(1-beta1^t), sqrt(1-beta2^t), inv_scale,
  * t (Adam's applied-step count, int bits)} (so the launch arguments are step-invariant and the launch can live in a
  * CUDA graph). */
@@ -186,8 +187,9 @@ int ngp_adam_hyper_update(int32_t* step_dev, float lr0, float lr_min, int32_t ma
 /* torch.cuda.amp.GradScaler.update() on the device (train.py:137-141,200): state_dev = {scale, growth_tracker};
  * found_inf != 0 -> scale *= backoff, tracker = 0; else tracker += 1 and, every growth_interval clean steps,
  * scale *= growth.  Also refreshes hyper_dev[2] = 1 / (scale * world_size) for the NEXT step's Adam. */
-int ngp_loss_scale_update(float* state_dev, const int32_t* found_inf, float growth, float backoff,
-                          int32_t growth_interval, float world_size, float* hyper_dev, void* stream);
+int ngp_loss_scale_update(float* state_dev, int32_t* found_inf, float growth, float backoff,
+                          int32_t growth_interval, float world_size, float* hyper_dev, int clear_found_inf,
+                          void* stream);
 /* the scalar housekeeping the reference does with tensor ops every step, in one launch (each pointer may be
  * NULL): counter[0:2] = 0 (modules/ray_march.py:183 `counter.zero_()`), *loss_sum = 0, *found_inf = 0
  * (GradScaler's per-step found_inf tensor), *batch_counter += 1 (batches drawn by ngp_sample_ray_batch) */

@@ -47,12 +47,12 @@ def _declare(lib):
         "ngp_hash_encode_bwd_input": (ci, [vp, vp, vp, ci, lay, vp, i64, vp]),
         "ngp_hash_encode_fwd_dyn": (ci, [vp, vp, lay, vp, ci, i64, vp, vp, vp]),
         "ngp_hash_encode_bwd_dyn": (ci, [vp, vp, ci, lay, vp, i64, vp, vp, vp]),
-        "ngp_hash_encode_bwd_levels": (ci, [vp, vp, ci, lay, vp, i64, vp, vp, ci, ci, vp]),
+        "ngp_hash_encode_bwd_levels": (ci, [vp, vp, ci, lay, vp, i64, vp, vp, ci, ci, vp, vp]),
         "ngp_mlp_fwd_dyn": (ci, [vp, ci, vp, mw, vp, vp, vp, i64, vp, vp]),
-        "ngp_mlp_bwd_dyn": (ci, [vp, ci, vp, mw, vp, vp, vp, vp, vp, i64, vp, vp]),
+        "ngp_mlp_bwd_dyn": (ci, [vp, ci, vp, mw, vp, vp, vp, vp, vp, i64, vp, vp, vp]),
         "ngp_adam_step_dyn": (ci, [vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, ci, i64, vp]),
         "ngp_adam_hyper_update": (ci, [vp, f32, f32, i32, f32, f32, f32, vp, vp, vp]),
-        "ngp_loss_scale_update": (ci, [vp, vp, f32, f32, i32, f32, vp, vp]),
+        "ngp_loss_scale_update": (ci, [vp, vp, f32, f32, i32, f32, vp, ci, vp]),
         "ngp_step_reset": (ci, [vp, vp, vp, vp, vp]),
         "ngp_mse_loss_grad_dyn": (ci, [vp, vp, vp, f32, vp, vp, vp, vp, i64, vp]),
         "ngp_mse_loss_grad": (ci, [vp, vp, vp, f32, f32, vp, vp, vp, i64, vp]),

@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
                                                             const T* __restrict__ dout,
                                                             const __grid_constant__ ngp_hash_layout lay,
                                                             float* __restrict__ grad_table, int64_t n_max,
-                                                            const Dyn dyn, int level_begin, int level_end) {
+                                                            const Dyn dyn, int level_begin, int level_end,
+                                                            int32_t* __restrict__ found_inf) {
     // blockDim.x = 32 * (level_end - level_begin): warp w scatters level level_begin + w (the multi-GPU step launches
     // the levels in groups so that a finished group's table slice is all-reduced while the next group runs)
     using V2 = typename Vec2<T>::type;
@@ -311,9 +312,13 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
     uint32_t pg[3] = {0u, 0u, 0u};
     float2 acc[8];
     bool pending = false;
+    bool bad = false;   // a non-finite contribution: raised at the source, so that no separate pass over the 45 MB
+                        // gradient buffer is needed for GradScaler's inf check (optional, found_inf may be NULL)
     auto flush = [&]() {
         uint32_t idx[8];
         corner_indices(m, pg, idx);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bad = bad || !(fabsf(acc[c].x) < INFINITY) || !(fabsf(acc[c].y) < INFINITY);
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
             if ((idx[c] ^ idx[c + 1]) == 1u) {  // x-neighbours in one aligned 16-byte block: one L2 atomic
@@ -356,6 +361,7 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const float* __restr
         }
     }
     if (pending) flush();
+    if (bad && found_inf != nullptr) *found_inf = 1;
 }
 
 // ---- generic feature width (F = 1..8, e.g. the reference's --deployment config L=4 F=4) -----------
@@ -565,12 +571,12 @@ int ngp_hash_encode_bwd(const float* xyz, const void* dout, int dout_dtype, cons
 int ngp_hash_encode_bwd_dyn(const float* xyz, const void* dout, int dout_dtype, const ngp_hash_layout* layout,
                             float* grad_table, int64_t n, const int32_t* n_dev, const float* aabb6, void* stream) {
     return ngp_hash_encode_bwd_levels(xyz, dout, dout_dtype, layout, grad_table, n, n_dev, aabb6, 0,
-                                      layout ? layout->n_levels : 0, stream);
+                                      layout ? layout->n_levels : 0, nullptr, stream);
 }
 
 int ngp_hash_encode_bwd_levels(const float* xyz, const void* dout, int dout_dtype, const ngp_hash_layout* layout,
                                float* grad_table, int64_t n, const int32_t* n_dev, const float* aabb6, int level_begin,
-                               int level_end, void* stream) {
+                               int level_end, int32_t* found_inf_or_null, void* stream) {
     const Dyn dyn = make_dyn(n_dev, aabb6);
     if (int rc = check_layout(layout)) return rc;
     NGP_REQUIRE(level_begin >= 0 && level_begin < level_end && level_end <= layout->n_levels, "bad level range");
@@ -594,9 +600,9 @@ int ngp_hash_encode_bwd_levels(const float* xyz, const void* dout, int dout_dtyp
     if (int rc = configure_smem()) return rc;
     const unsigned threads = 32u * (unsigned)(level_end - level_begin);
     if (dout_dtype == NGP_F16)
-        hash_bwd_kernel<__half><<<grid, threads, smem_bytes(layout->n_levels, 4), st>>>(xyz, (const __half*)dout, *layout, grad_table, n, dyn, level_begin, level_end);
+        hash_bwd_kernel<__half><<<grid, threads, smem_bytes(layout->n_levels, 4), st>>>(xyz, (const __half*)dout, *layout, grad_table, n, dyn, level_begin, level_end, found_inf_or_null);
     else
-        hash_bwd_kernel<float><<<grid, threads, smem_bytes(layout->n_levels, 8), st>>>(xyz, (const float*)dout, *layout, grad_table, n, dyn, level_begin, level_end);
+        hash_bwd_kernel<float><<<grid, threads, smem_bytes(layout->n_levels, 8), st>>>(xyz, (const float*)dout, *layout, grad_table, n, dyn, level_begin, level_end, found_inf_or_null);
     NGP_LAUNCHED("hash_bwd_kernel");
     return 0;
 }

@@ -386,7 +386,8 @@ __global__ void __launch_bounds__(kThreadsBwd, 2) mlp_bwd_kernel(const TEmb* __r
                                                            const float* __restrict__ dsigmas,
                                                            const __half* __restrict__ drgbs, TEmb* __restrict__ demb,
                                                            float* __restrict__ grad_w, int64_t n_max,
-                                                           const int32_t* __restrict__ n_dev) {
+                                                           const int32_t* __restrict__ n_dev,
+                                                           int32_t* __restrict__ found_inf) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int64_t n = n_dev ? min(n_max, max((int64_t)*n_dev, (int64_t)0)) : n_max;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & (kRows - 1), hh = tid >> 7;
@@ -604,10 +605,16 @@ __global__ void __launch_bounds__(kThreadsBwd, 2) mlp_bwd_kernel(const TEmb* __r
         const int m = warp * 16 + lane;  // row held by this thread when lane < 16
         const bool has_row = lane < 16;
         float v[16];
+        bool bad = false;   // non-finite weight gradient (GradScaler's inf check, raised at the source)
+        auto chk = [&]() {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) bad = bad || !(fabsf(v[j]) < INFINITY);
+        };
         // dW4 [64 out x 64 in]
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             tmem_ld16(tmem_row + kColDW4 + g * 16, v);
+            if (has_row) chk();
             if (has_row)
 #pragma unroll
                 for (int j = 0; j < 16; ++j) atomicAdd(grad_w + (NGP_MLP_W1 + NGP_MLP_W2 + NGP_MLP_W3) + m * 64 + g * 16 + j, v[j]);
@@ -616,24 +623,29 @@ __global__ void __launch_bounds__(kThreadsBwd, 2) mlp_bwd_kernel(const TEmb* __r
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
             tmem_ld16(tmem_row + kColDW1 + g * 16, v);
+            if (has_row) chk();
             if (has_row)
 #pragma unroll
                 for (int j = 0; j < 16; ++j) atomicAdd(grad_w + m * 32 + g * 16 + j, v[j]);
             tmem_ld16(tmem_row + kColDW3 + g * 16, v);
+            if (has_row) chk();
             if (has_row)
 #pragma unroll
                 for (int j = 0; j < 16; ++j) atomicAdd(grad_w + (NGP_MLP_W1 + NGP_MLP_W2) + m * 32 + g * 16 + j, v[j]);
         }
         // dW2^T [64 in x 16 out] -> W2 is [16 out x 64 in]
         tmem_ld16(tmem_row + kColDW2T, v);
+        if (has_row) chk();
         if (has_row)
 #pragma unroll
             for (int j = 0; j < 16; ++j) atomicAdd(grad_w + NGP_MLP_W1 + j * 64 + m, v[j]);
         // dW5^T [64 in x 16 (3 used)] -> W5 is [3 out x 64 in]
         tmem_ld16(tmem_row + kColDW5T, v);
+        if (has_row) chk();   // columns 3..15 hold products with the zero padding of dO: finite unless dO is not
         if (has_row)
 #pragma unroll
             for (int j = 0; j < 3; ++j) atomicAdd(grad_w + (NGP_MLP_W1 + NGP_MLP_W2 + NGP_MLP_W3 + NGP_MLP_W4) + j * 64 + m, v[j]);
+        if (bad && found_inf != nullptr) *found_inf = 1;
     }
     tc_fence_before();
     __syncthreads();
@@ -642,7 +654,8 @@ __global__ void __launch_bounds__(kThreadsBwd, 2) mlp_bwd_kernel(const TEmb* __r
 
 template <typename TEmb, bool kSaved>
 int launch_bwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, const void* save, const float* dsigmas,
-               const void* drgbs, void* demb, float* grad_w, int64_t n, const int32_t* n_dev, cudaStream_t st) {
+               const void* drgbs, void* demb, float* grad_w, int64_t n, const int32_t* n_dev, int32_t* found_inf,
+               cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel<TEmb, kSaved>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -658,7 +671,7 @@ int launch_bwd(const void* emb, const float* dirs, const ngp_mlp_weights* w, con
     const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
     mlp_bwd_kernel<TEmb, kSaved><<<grid, kThreadsBwd, kSmemBytesBwd, st>>>((const TEmb*)emb, dirs, *w, (const __half*)save,
                                                                        dsigmas, (const __half*)drgbs, (TEmb*)demb,
-                                                                       grad_w, n, n_dev);
+                                                                       grad_w, n, n_dev, found_inf);
     NGP_LAUNCHED("mlp_bwd_kernel");
     return 0;
 }
@@ -747,12 +760,12 @@ int ngp_mlp_fwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp
 
 int ngp_mlp_bwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
                 const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n, void* stream) {
-    return ngp_mlp_bwd_dyn(emb, emb_dtype, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, nullptr, stream);
+    return ngp_mlp_bwd_dyn(emb, emb_dtype, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, nullptr, nullptr, stream);
 }
 
 int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w, const void* save,
                     const float* dsigmas, const void* drgbs_f16, void* demb, float* grad_w, int64_t n,
-                    const int32_t* n_dev, void* stream) {
+                    const int32_t* n_dev, int32_t* found_inf_or_null, void* stream) {
     NGP_REQUIRE(n >= 0, "negative n");
     if (n == 0) return 0;
     if (int rc = check_mlp_args(emb, emb_dtype, dirs, w)) return rc;
@@ -761,11 +774,11 @@ int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp
     NGP_REQUIRE((reinterpret_cast<uintptr_t>(save) & 15) == 0, "save must be 16-byte aligned");
     cudaStream_t st = ngp::as_stream(stream);
     if (emb_dtype == NGP_F16) {
-        return save ? launch_bwd<__half, true>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st)
-                    : launch_bwd<__half, false>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st);
+        return save ? launch_bwd<__half, true>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, found_inf_or_null, st)
+                    : launch_bwd<__half, false>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, found_inf_or_null, st);
     }
-    return save ? launch_bwd<float, true>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st)
-                : launch_bwd<float, false>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, st);
+    return save ? launch_bwd<float, true>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, found_inf_or_null, st)
+                : launch_bwd<float, false>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, found_inf_or_null, st);
 }
 
 }  // extern "C"

@@ -107,8 +107,9 @@ __global__ void step_reset_kernel(int32_t* __restrict__ counter2, float* __restr
 }
 
 // GradScaler.update(): torch/amp/grad_scaler.py -> _amp_update_scale_
-__global__ void loss_scale_update_kernel(float* __restrict__ state, const int32_t* __restrict__ found_inf, float growth,
-                                         float backoff, int32_t interval, float world, float* __restrict__ hyper) {
+__global__ void loss_scale_update_kernel(float* __restrict__ state, int32_t* __restrict__ found_inf, float growth,
+                                         float backoff, int32_t interval, float world, float* __restrict__ hyper,
+                                         int clear_found_inf) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float scale = state[0];
     int32_t tracker = __float_as_int(state[1]);
@@ -126,6 +127,8 @@ __global__ void loss_scale_update_kernel(float* __restrict__ state, const int32_
     state[0] = scale;
     state[1] = __int_as_float(tracker);
     if (hyper != nullptr) hyper[2] = 1.0f / (scale * world);
+    // last reader of the step's flag: hand a clean one to the next backward (kernels that raise it at the source)
+    if (clear_found_inf && found_inf != nullptr) *found_inf = 0;
 }
 
 __global__ void __launch_bounds__(256) check_finite_kernel(const float* __restrict__ grad, int64_t n,
@@ -213,12 +216,13 @@ int ngp_adam_hyper_update(int32_t* step_dev, float lr0, float lr_min, int32_t ma
     return 0;
 }
 
-int ngp_loss_scale_update(float* state_dev, const int32_t* found_inf, float growth, float backoff,
-                          int32_t growth_interval, float world_size, float* hyper_dev, void* stream) {
+int ngp_loss_scale_update(float* state_dev, int32_t* found_inf, float growth, float backoff,
+                          int32_t growth_interval, float world_size, float* hyper_dev, int clear_found_inf,
+                          void* stream) {
     NGP_REQUIRE(state_dev != nullptr, "null pointer");
     NGP_REQUIRE(growth >= 1.0f && backoff > 0.0f && backoff <= 1.0f && growth_interval >= 1, "bad GradScaler constants");
     loss_scale_update_kernel<<<1, 32, 0, ngp::as_stream(stream)>>>(state_dev, found_inf, growth, backoff, growth_interval,
-                                                                   world_size, hyper_dev);
+                                                                   world_size, hyper_dev, clear_found_inf);
     NGP_LAUNCHED("loss_scale_update_kernel");
     return 0;
 }

@@ -92,6 +92,11 @@ class StaticTrainStep:
         self._side = torch.cuda.Stream(device=dev, priority=-1)
         self._ar_stream = torch.cuda.Stream(device=dev)
         # several ranks: all-reduce gradient slices behind the backward kernels that complete them (stock F = 2 layout)
+        # one rank + dynamic loss scale: the backward kernels raise GradScaler's inf flag themselves (a non-finite
+        # contribution is seen where it is scattered), the optimizer consumes and clears it - no 45 MB check pass
+        self.inf_at_source = bool(trainer.world_size == 1 and self.dynamic_loss_scale and enc._clayout.feat_dim == 2)
+        if self.inf_at_source:
+            trainer.found_inf.zero_()
         import os
         default_ar = trainer.world_size > 1 and enc._clayout.feat_dim == 2 and os.environ.get("NGP_AR_OVERLAP", "1") != "0"
         self.overlap_allreduce = bool(overlap_allreduce if overlap_allreduce is not None else default_ar)
@@ -171,14 +176,16 @@ class StaticTrainStep:
         L, st, tag = load(), self._st(), (F16 if self.half else F32)
         gw = self.tr.flat_grad[self.P:self.P + 9408]
         check(L.ngp_mlp_bwd_dyn(_p(self.emb), tag, _p(self.dirs), C.byref(self._wst), _p(self.mlp_save), _p(self.dsig),
-                                _p(self.drgbs), _p(self.demb), _p(gw), self.cap, _p(self.counter), st))
+                                _p(self.drgbs), _p(self.demb), _p(gw), self.cap, _p(self.counter),
+                                _p(self.tr.found_inf) if self.inf_at_source else None, st))
 
     def _k_hash_bwd(self, level_begin=0, level_end=None):
         L, st, tag = load(), self._st(), (F16 if self.half else F32)
         level_end = self._clayout.n_levels if level_end is None else level_end
         check(L.ngp_hash_encode_bwd_levels(_p(self.xyzs), _p(self.demb), tag, C.byref(self._clayout),
                                            _p(self.tr.flat_grad), self.cap, _p(self.counter), self.aabb6,
-                                           int(level_begin), int(level_end), st))
+                                           int(level_begin), int(level_end),
+                                           _p(self.tr.found_inf) if self.inf_at_source else None, st))
 
     def _level_groups(self):
         """Level groups of the multi-GPU backward, most expensive first: the hashed fine levels (all-distinct cells,
@@ -241,14 +248,16 @@ class StaticTrainStep:
     def _enqueue_update(self):
         # [all-reduce, unless the backward already reduced slice by slice] -> check_finite -> LR/bias scalars ->
         # fused Adam -> GradScaler.update
-        self.tr.enqueue_update(allreduce=not self.overlap_allreduce)
+        self.tr.enqueue_update(allreduce=not self.overlap_allreduce, check_finite=not self.inf_at_source)
 
     def _enqueue(self, sampled=False, mode="sync"):
         if sampled:
             self._enqueue_sampler()
         # march counter, loss accumulator, found_inf <- 0 and (own batch counter: step_dev moves with the optimizer,
         # which may run a step late) sample_step += 1, in one launch
-        check(load().ngp_step_reset(_p(self.counter), _p(self.loss_sum), _p(self.tr.found_inf),
+        # (with inf_at_source the flag is raised by the previous backward and cleared by its consumer, the optimizer)
+        check(load().ngp_step_reset(_p(self.counter), _p(self.loss_sum),
+                                    None if self.inf_at_source else _p(self.tr.found_inf),
                                     _p(self.sample_step) if sampled else None, self._st()))
         if mode == "steady":
             # optimizer of the PREVIOUS step beside this step's ray_aabb + marching.  The marching branch runs on
@@ -326,7 +335,8 @@ class StaticTrainStep:
         """Overlap mode: apply the optimizer update of the last step now (before anything reads the parameters:
         update_density_grid, rendering, checkpoints).  No-op otherwise."""
         if self.pending:
-            self.tr.found_inf.zero_()
+            if not self.inf_at_source:
+                self.tr.found_inf.zero_()
             self._enqueue_update()
             self.pending = False
             if self.tr._shadow is not None:

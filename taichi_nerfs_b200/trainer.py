@@ -122,14 +122,15 @@ class NGPTrainer:
         (loss * scale).backward()
         return loss, results
 
-    def enqueue_update(self, allreduce: bool = True):
+    def enqueue_update(self, allreduce: bool = True, check_finite: bool = True):
         """[all-reduce] -> inf check -> LR / bias-correction scalars -> fused Adam (+fp16 shadow, grad zero) ->
         GradScaler.update(), all on the current stream with device-side scalars (graph-capturable)."""
         L, st = load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
         fg = self.flat_grad
         if allreduce:
             parallel.allreduce_gradients(fg, self.pg)
-        check(L.ngp_check_finite(_p(fg), fg.numel(), _p(self.found_inf), st))   # after the sum: identical on every rank
+        if check_finite:   # (False: the backward kernels already raised the flag at the source, fast_step.py)
+            check(L.ngp_check_finite(_p(fg), fg.numel(), _p(self.found_inf), st))   # after the sum: identical on every rank
         # inv_scale: static (host constant) or the device value maintained by ngp_loss_scale_update (-1 sentinel)
         inv = -1.0 if self.dynamic_loss_scale else parallel.inv_grad_scale(self.loss_scale, self.world_size)
         check(L.ngp_adam_hyper_update(_p(self.step_dev), self.lr0, self.lr0 / 30, self.max_steps, self.betas[0],
@@ -140,7 +141,7 @@ class NGPTrainer:
                                   self.betas[1], self.eps, 1, fg.numel(), st))
         if self.dynamic_loss_scale:  # GradScaler.update(): adjusts the scale used by the NEXT step
             check(L.ngp_loss_scale_update(_p(self.scale_state), _p(self.found_inf), 2.0, 0.5, 2000,
-                                          float(self.world_size), _p(self.hyper), st))
+                                          float(self.world_size), _p(self.hyper), 0 if check_finite else 1, st))
 
     def optimizer_step(self):
         self.check_aliasing()
