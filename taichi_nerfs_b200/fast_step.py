@@ -91,15 +91,21 @@ class StaticTrainStep:
         self.pending = False             # gradients of the last step not applied yet (overlap mode only)
         self._side = torch.cuda.Stream(device=dev, priority=-1)
         self._ar_stream = torch.cuda.Stream(device=dev)
-        # several ranks: all-reduce gradient slices behind the backward kernels that complete them (stock F = 2 layout)
+        # several ranks, opt-in: all-reduce gradient slices behind the backward kernels that complete them (F = 2 layout)
+        import os
+        # (opt-in, NGP_AR_OVERLAP=1: on 2 GPUs the three grouped scatter launches + concurrent NCCL kernels cost more
+        # than the all-reduce they hide — profiles/r2_bench_2gpu_*.json)
+        default_ar = ((trainer.world_size > 1 or os.environ.get("NGP_AR_FORCE") == "1") and enc._clayout.feat_dim == 2
+                      and os.environ.get("NGP_AR_OVERLAP", "0") == "1")
+        self.overlap_allreduce = bool(overlap_allreduce if overlap_allreduce is not None else default_ar)
+        if self.overlap_allreduce and trainer.sharded:
+            trainer.sharded = False     # the slice all-reduces replace the reduce-scatter; Adam stays replicated
         # one rank + dynamic loss scale: the backward kernels raise GradScaler's inf flag themselves (a non-finite
         # contribution is seen where it is scattered), the optimizer consumes and clears it - no 45 MB check pass
-        self.inf_at_source = bool(trainer.world_size == 1 and self.dynamic_loss_scale and enc._clayout.feat_dim == 2)
+        self.inf_at_source = bool((trainer.world_size == 1 or trainer.sharded) and self.dynamic_loss_scale
+                                  and enc._clayout.feat_dim == 2)
         if self.inf_at_source:
             trainer.found_inf.zero_()
-        import os
-        default_ar = trainer.world_size > 1 and enc._clayout.feat_dim == 2 and os.environ.get("NGP_AR_OVERLAP", "1") != "0"
-        self.overlap_allreduce = bool(overlap_allreduce if overlap_allreduce is not None else default_ar)
         self.use_graph = bool(use_graph)
         if self.use_graph:
             try:
@@ -341,6 +347,7 @@ class StaticTrainStep:
             self.pending = False
             if self.tr._shadow is not None:
                 self.model.pos_encoder.adopt_shadow(self.tr._shadow)
+        self.tr.sync_master()   # sharded optimizer: the fp32 master table is complete again on every rank
 
     def _finish_step(self):
         self.tr.step_count += 1

@@ -45,3 +45,13 @@ def allreduce_found_inf(found_inf: torch.Tensor, group=None) -> torch.Tensor:
 def inv_grad_scale(loss_scale: float, world: int) -> float:
     """Factor that turns the all-reduced, loss-scaled gradient sum into the global-batch mean gradient."""
     return 1.0 / (float(loss_scale) * world)
+
+
+def optimizer_shard(n_table: int, rank: int, world: int):
+    """[begin, end) of the flat table parameter owned by ``rank`` in the sharded optimizer (NGPTrainer): equal shards,
+    each a multiple of 4 floats so that every shard stays 16-byte aligned for the float4 Adam sweep."""
+    if n_table % (4 * world) != 0:
+        raise ValueError(f"table size {n_table} is not a multiple of 4 * world ({world})")
+    shard = n_table // world
+    return rank * shard, (rank + 1) * shard
+

@@ -30,7 +30,8 @@ def _p(t):
 
 class NGPTrainer:
     def __init__(self, model, lr: float = 1e-2, max_steps: int = 20000, loss_scale: float | None = None,
-                 betas=(0.9, 0.999), eps: float = 1e-15, process_group=None, dynamic_loss_scale: bool = True):
+                 betas=(0.9, 0.999), eps: float = 1e-15, process_group=None, dynamic_loss_scale: bool = True,
+                 sharded_optimizer: bool | None = None):
         self.model = model
         self.lr0 = lr
         self.max_steps = max_steps
@@ -85,6 +86,25 @@ class NGPTrainer:
             self._shadow = self._shadow_full[:enc.hash_table.numel()]
             enc.adopt_shadow(self._shadow)
 
+        # Several ranks, fp16 encoder: shard the optimizer over the hash table (the MLP weights stay replicated).
+        # Per step: reduce-scatter of the table gradient (each rank receives the sum for the entries it owns), Adam on
+        # the owned 1/N of the table, all-gather of the updated fp16 shadow (what the kernels read) — 0.75x the bytes
+        # of an all-reduce and 1/N of the Adam sweep.  The fp32 master of non-owned entries goes stale until
+        # sync_master() (called before state_dict / checkpoints).
+        import os
+        P = self.slices[0][1]
+        want = (sharded_optimizer if sharded_optimizer is not None
+                else os.environ.get("NGP_SHARDED_ADAM", "1") != "0")
+        self.sharded = bool(want and self.world_size > 1 and self._shadow_full is not None
+                            and P % (4 * self.world_size) == 0 and self.slices[0][0] == 0)
+        if self.sharded:
+            self.rank = torch.distributed.get_rank(process_group)
+            self.shard_lo, hi = parallel.optimizer_shard(P, self.rank, self.world_size)
+            self.shard = hi - self.shard_lo
+            self.grad_shard = torch.zeros(self.shard, device=dev, dtype=torch.float32)
+            self.shadow_shard = torch.zeros(self.shard, device=dev, dtype=torch.float16)
+            self.master_stale = False
+
     # cosine annealing to lr/30 (train.py:159-163, CosineAnnealingLR(T_max=max_steps, eta_min=lr/30))
     def lr_at(self, step: int) -> float:
         eta_min = self.lr0 / 30
@@ -125,6 +145,8 @@ class NGPTrainer:
     def enqueue_update(self, allreduce: bool = True, check_finite: bool = True):
         """[all-reduce] -> inf check -> LR / bias-correction scalars -> fused Adam (+fp16 shadow, grad zero) ->
         GradScaler.update(), all on the current stream with device-side scalars (graph-capturable)."""
+        if self.sharded and allreduce:
+            return self._enqueue_update_sharded(check_finite)
         L, st = load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
         fg = self.flat_grad
         if allreduce:
@@ -142,6 +164,44 @@ class NGPTrainer:
         if self.dynamic_loss_scale:  # GradScaler.update(): adjusts the scale used by the NEXT step
             check(L.ngp_loss_scale_update(_p(self.scale_state), _p(self.found_inf), 2.0, 0.5, 2000,
                                           float(self.world_size), _p(self.hyper), 0 if check_finite else 1, st))
+
+    def _enqueue_update_sharded(self, check_finite: bool):
+        """Sharded update (see __init__): inf flag (local check, max over ranks) -> reduce-scatter of the table gradient
+        + all-reduce of the MLP gradients -> Adam on the owned table shard and on the replicated MLP weights ->
+        all-gather of the fp16 shadow table -> GradScaler.update()."""
+        import torch.distributed as dist
+        L, st = load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        fg, P, lo, hi = self.flat_grad, self.slices[0][1], self.shard_lo, self.shard_lo + self.shard
+        if check_finite:   # on the local gradient: a non-finite term on any rank makes the sum non-finite
+            check(L.ngp_check_finite(_p(fg), fg.numel(), _p(self.found_inf), st))
+        dist.all_reduce(self.found_inf, op=dist.ReduceOp.MAX, group=self.pg)
+        dist.reduce_scatter_tensor(self.grad_shard, fg[:P], op=dist.ReduceOp.SUM, group=self.pg)
+        dist.all_reduce(fg[P:], op=dist.ReduceOp.SUM, group=self.pg)
+        inv = -1.0 if self.dynamic_loss_scale else parallel.inv_grad_scale(self.loss_scale, self.world_size)
+        check(L.ngp_adam_hyper_update(_p(self.step_dev), self.lr0, self.lr0 / 30, self.max_steps, self.betas[0],
+                                      self.betas[1], inv, _p(self.found_inf), _p(self.hyper), st))
+        check(L.ngp_adam_step_dyn(_p(self.flat_param[lo:hi]), _p(self.grad_shard), _p(self.exp_avg[lo:hi]),
+                                  _p(self.exp_avg_sq[lo:hi]), _p(self.shadow_shard), _p(self.found_inf), _p(self.hyper),
+                                  self.betas[0], self.betas[1], self.eps, 0, self.shard, st))
+        check(L.ngp_adam_step_dyn(_p(self.flat_param[P:]), _p(fg[P:]), _p(self.exp_avg[P:]), _p(self.exp_avg_sq[P:]),
+                                  _p(self._shadow_full[P:]), _p(self.found_inf), _p(self.hyper), self.betas[0],
+                                  self.betas[1], self.eps, 1, fg.numel() - P, st))
+        fg[:P].zero_()     # the local table gradient (the Adam sweep only saw the reduced shard)
+        dist.all_gather_into_tensor(self._shadow_full[:P], self.shadow_shard, group=self.pg)
+        if self.dynamic_loss_scale:
+            check(L.ngp_loss_scale_update(_p(self.scale_state), _p(self.found_inf), 2.0, 0.5, 2000,
+                                          float(self.world_size), _p(self.hyper), 0 if check_finite else 1, st))
+        self.master_stale = True
+
+    def sync_master(self):
+        """Sharded optimizer: make the fp32 master table complete on every rank again (before state_dict(), checkpoints
+        or anything else that reads ``hash_table`` itself rather than the fp16 shadow)."""
+        if getattr(self, 'sharded', False) and self.master_stale:
+            import torch.distributed as dist
+            P, lo = self.slices[0][1], self.shard_lo
+            own = self.flat_param[lo:lo + self.shard].clone()
+            dist.all_gather_into_tensor(self.flat_param[:P], own, group=self.pg)
+            self.master_stale = False
 
     def optimizer_step(self):
         self.check_aliasing()
