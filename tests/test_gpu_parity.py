@@ -382,14 +382,18 @@ def test_mlp_bwd_tcgen05_matches_oracle(ops, oracle, emb_half, n, saved):
     demb, gw = ops.mlp_bwd(T(emb), T(dirs), [T(w) for w in ws], T(dsig), T(drgb), save=save)
     demb, gw = N(demb).astype(np.float32), N(gw)
     demb_ref = demb_ref.astype(np.float32)
-    # every intermediate gradient is rounded to fp16 on both sides; the tensor core sums K in a
-    # different order, so individual fp16 roundings can flip by 1 ulp (2^-11 relative): 5e-3 of the
-    # tensor's max magnitude bounds the propagated effect (north_star: 1e-3 relative on gradients
-    # is checked on the median below)
-    assert np.abs(demb - demb_ref).max() <= 5e-3 * np.abs(demb_ref).max()
+    # Error model (measured: profiles/r2_mlp_bwd_error.txt).  Every intermediate gradient is rounded to fp16 on both
+    # sides and the tensor core sums K in a different order, so individual roundings flip by one fp16 ulp: the bulk of
+    # the elements agrees to ~2e-5 of the tensor's max (asserted on the 99.9th percentile at 1e-4 = 5x measured).  The
+    # few large deviations are not rounding noise but ReLU-mask flips: a hidden pre-activation within an ulp of zero is
+    # positive on one side and zero on the other, which switches a whole path of the backward on or off; measured
+    # up to 3.0e-3 of max on demb and on the dW3 / dW4 blocks at n = 40000, asserted at 5e-3.
+    err = np.abs(demb - demb_ref)
+    assert np.percentile(err, 99.9) <= 1e-4 * np.abs(demb_ref).max()
+    assert err.max() <= 5e-3 * np.abs(demb_ref).max()
     assert np.abs(gw - gw_ref).max() <= 5e-3 * np.abs(gw_ref).max()
     big = np.abs(gw_ref) > 0.05 * np.abs(gw_ref).max()
-    assert np.median(np.abs(gw[big] - gw_ref[big]) / np.abs(gw_ref[big])) < 1e-3
+    assert np.median(np.abs(gw[big] - gw_ref[big]) / np.abs(gw_ref[big])) < 1e-4       # measured ~2e-5
     # per-layer blocks must all be populated (catches a transposed / misplaced dW block)
     offs = np.cumsum([0, 2048, 1024, 2048, 4096, 192])
     for a, b in zip(offs[:-1], offs[1:]):
