@@ -611,6 +611,10 @@ def run_frame(args, cfg_name, cfg):
     launches = _lib.launch_count() - launches0
     clock_info = clocks.stop()
     total_samples = int(res["total_samples"])
+    fr = next(iter(model.__dict__.get("_frame_renderers", {}).values()), None)
+    if fr is not None and fr.coarse is not None:   # how much of the box the empty-space leap has to respect
+        words = fr.coarse.cpu().numpy().view(np.uint32)
+        info["coarse_supercells_occupied"] = float(sum(bin(int(x)).count("1") for x in words)) / (32 * len(words))
 
     def e2e_frame():
         p = pose_host.to(dev, non_blocking=True)

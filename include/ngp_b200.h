@@ -301,9 +301,9 @@ int ngp_raymarching_round(const float* rays_o, const float* rays_d, const float*
                           int32_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts, int64_t n_rays,
                           int64_t capacity, const uint32_t* coarse_or_null, void* stream);
 /* Optional accelerator of the round march for one-cascade, constant-step scenes: coarse[(G/8)^3 / 32 words], bit s =
- * the 8^3-cell super-cell with Morton index s, or one of its 26 neighbours, holds an occupied cell.  With it the march
- * leaps over 256 candidate positions at a time where the ray crosses empty space; the emitted samples are unchanged
- * (bit-exact: the leap is taken only where the reference loop would visit every position and emit nothing). */
+ * the 8^3-cell super-cell with Morton index s holds an occupied cell.  With it the march leaps over up to 256
+ * candidate positions at a time where the ray crosses empty space; the emitted samples are unchanged (bit-exact: the
+ * leap is taken only where the reference loop would visit every position and emit nothing). */
 int ngp_build_coarse_occupancy(const uint8_t* density_bitfield, int grid_size, uint32_t* coarse, void* stream);
 /* composite_test (modules/volume_render_test.py:4-54) for the round's samples, accumulating into opacity/depth/rgb
  * [n_rays], + block-level compaction of the rays that stay alive (T > T_threshold and still inside the box) into
@@ -381,6 +381,15 @@ int ngp_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                   int32_t step, int zero_grad, int64_t n, void* stream);
 /* sets *found_inf = 1 if any element of grad is non-finite (GradScaler check) */
 int ngp_check_finite(const float* grad, int64_t n, int32_t* found_inf, void* stream);
+/* Multi-GPU gradient transport in fp16 (what the reference's autocast backward produces for its parameters; the
+ * loss scale keeps the values in range and a value that does not fit becomes inf, i.e. a skipped step + scale backoff
+ * exactly as with GradScaler): pack the fp32 accumulation buffer, all-reduce the fp16 buffer (half the bytes), check
+ * the REDUCED buffer (identical on every rank) and let Adam read it directly while zeroing the fp32 buffer. */
+int ngp_grad_pack_f16(const float* grad, void* out_f16, int64_t n, void* stream);
+int ngp_check_finite_f16(const void* grad_f16, int64_t n, int32_t* found_inf, void* stream);
+int ngp_adam_step_dyn_g16(float* param, const void* grad_f16, float* grad_f32_to_zero_or_null, float* exp_avg,
+                          float* exp_avg_sq, void* param_f16_or_null, const int32_t* found_inf_or_null,
+                          const float* hyper_dev, float beta1, float beta2, float eps, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,8 @@ bits = np.load(os.path.join(ROOT, "tests", "golden", "lego_bitfield.npz"))["bitf
 thr = 0.01 * 1024 / 3 ** 0.5
 
 
-def run(sharded, overlap_ar, overlap_opt):
+def run(sharded, overlap_ar, overlap_opt, f16=False):
+    os.environ["NGP_GRAD_F16"] = "1" if f16 else "0"
     torch.manual_seed(3)
     m = NGP(scale=0.5, max_res=1024, half_opt=True).cuda()
     with torch.no_grad():
@@ -32,7 +33,7 @@ def run(sharded, overlap_ar, overlap_opt):
         m.density_bitfield.copy_(torch.from_numpy(bits))
     tr = NGPTrainer(m, lr=1e-2, sharded_optimizer=sharded)
     fs = StaticTrainStep(tr, 4096, samples_per_ray_capacity=64, overlap_allreduce=overlap_ar, overlap_optimizer=overlap_opt)
-    assert tr.sharded == (sharded and not overlap_ar)
+    assert tr.sharded == (sharded and not overlap_ar) and tr.grad_f16 == (f16 and not sharded)
     losses = []
     for k in range(4):
         o, d = make_rays(4096, seed=100 * rank + k)          # every rank renders its own shard
@@ -52,13 +53,14 @@ m1, t1, l1 = run(False, False, False)     # replicated Adam, one monolithic all-
 m2, t2, l2 = run(True, False, False)      # sharded optimizer: reduce-scatter, shard Adam, all-gather of the fp16 shadow
 m3, t3, l3 = run(True, False, True)       # + optimizer of step k beside the marching of step k+1
 m4, t4, l4 = run(False, True, False)      # opt-in: slice all-reduces behind the level groups of the hash backward
+m5, t5, l5 = run(False, False, True, f16=True)   # default at N > 1: fp16 gradient transport + optimizer overlap
 for name, (ma, mb) in {"sharded vs replicated": (m1, m2), "sharded + optimizer overlap": (m1, m3),
-                       "slice all-reduce vs monolithic": (m1, m4)}.items():
+                       "slice all-reduce vs monolithic": (m1, m4), "fp16 transport vs fp32": (m1, m5)}.items():
     for pa, pb in zip(ma.parameters(), mb.parameters()):
         bad = float(((pa - pb).abs() > 2e-3).float().mean())
         assert bad < 2e-3, (name, bad)
 # replicas agree bit for bit: parameters and occupancy grids
-for m in (m1, m2, m3, m4):
+for m in (m1, m2, m3, m4, m5):
     flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
     ref = flat.clone()
     dist.broadcast(ref, 0)
@@ -68,5 +70,5 @@ for m in (m1, m2, m3, m4):
     dist.broadcast(gr, 0)
     assert torch.equal(g, gr), "occupancy bitfields differ across ranks"
 if rank == 0:
-    print(f"dist check ok on {world} GPUs: losses {l1} / {l2} / {l3} / {l4}")
+    print(f"dist check ok on {world} GPUs: losses {l1} / {l2} / {l3} / {l4} / {l5}")
 dist.destroy_process_group()

@@ -75,6 +75,9 @@ def _declare(lib):
         "ngp_morton3d_invert": (ci, [vp, vp, i64, vp]),
         "ngp_adam_step": (ci, [vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, ci, i64, vp]),
         "ngp_check_finite": (ci, [vp, i64, vp, vp]),
+        "ngp_grad_pack_f16": (ci, [vp, vp, i64, vp]),
+        "ngp_check_finite_f16": (ci, [vp, i64, vp, vp]),
+        "ngp_adam_step_dyn_g16": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, i64, vp]),
         "ngp_frame_begin": (ci, [vp, vp, vp, vp, vp, vp, vp, i64, vp]),
         "ngp_frame_round_begin": (ci, [vp, vp]),
         "ngp_raymarching_round": (ci, [vp, vp, vp, vp, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp]),

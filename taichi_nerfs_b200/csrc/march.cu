@@ -271,8 +271,8 @@ __device__ __forceinline__ void march_one_ray(const float* __restrict__ rays_o, 
     const float dt0 = calc_dt(t, p.esf, p.dt_max);
 
     // Empty-space leap (constant step, one cascade, coarse occupancy available): up to 256 candidate positions at once.
-    // Lane j looks at position 8j; if the DILATED super-cell (8^3 cells + its 26 neighbours) there is empty, positions
-    // 8j .. 8j+7 lie in empty cells (they are < 8 cells away per axis).  If the first position is "regular" (an axis
+    // Lane j looks at positions 8j and 8j+7; if every 8^3-cell super-cell in the box spanned by their two super-cells
+    // is empty, positions 8j .. 8j+7 (collinear) lie in empty cells.  If the first position is "regular" (an axis
     // with d < -1e-3 and an unclamped coordinate, which only decreases along the ray) the reference loop visits every
     // position, emits nothing in empty cells and advances by exactly one step each (tests/test_oracle.py, exit quirk),
     // so with f leading lanes vouching t jumps to position 8f by the closed form of the fp32 recurrence.
@@ -298,17 +298,31 @@ __device__ __forceinline__ void march_one_ray(const float* __restrict__ rays_o, 
                 const bool in_binade = m + (uint32_t)(8 * lane + 8) * cs <= 0xffffffu;
                 const float tq = __uint_as_float((e << 23) | ((m + (uint32_t)(8 * lane) * cs) & 0x7fffffu));
                 const float tl = __uint_as_float((e << 23) | ((m + (uint32_t)(8 * lane + 7) * cs) & 0x7fffffu));
+                // cells of the first (p) and last (q) position of this lane's range; the six positions in between lie
+                // on the segment p-q, so their cells are inside the box spanned by the two cells, i.e. inside the (at
+                // most 2x2x2) super-cells spanned by the two super-cells
                 bool reg = false;
-                uint32_t u[3];
+                uint32_t sa[3], sb[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float x = f_add(ray.o[k], f_mul(tq, ray.d[k]));
-                    const float raw = f_mul(f_mul(0.5f, f_add(f_mul(x, mb0_inv), 1.0f)), p.gsf);
-                    reg = reg || (ray.d[k] < -1e-3f && raw < f_sub(p.gsf, 1.0f));
-                    u[k] = __float2uint_rz(fminf(fmaxf(raw, 0.0f), f_sub(p.gsf, 1.0f)));
+                    const float xp = f_add(ray.o[k], f_mul(tq, ray.d[k]));
+                    const float xq = f_add(ray.o[k], f_mul(tl, ray.d[k]));
+                    const float rp = f_mul(f_mul(0.5f, f_add(f_mul(xp, mb0_inv), 1.0f)), p.gsf);
+                    const float rq = f_mul(f_mul(0.5f, f_add(f_mul(xq, mb0_inv), 1.0f)), p.gsf);
+                    reg = reg || (ray.d[k] < -1e-3f && rp < f_sub(p.gsf, 1.0f));
+                    const uint32_t up = __float2uint_rz(fminf(fmaxf(rp, 0.0f), f_sub(p.gsf, 1.0f))) >> 3;
+                    const uint32_t uq = __float2uint_rz(fminf(fmaxf(rq, 0.0f), f_sub(p.gsf, 1.0f))) >> 3;
+                    sa[k] = min(up, uq);
+                    sb[k] = max(up, uq);
                 }
-                const uint32_t sc = morton3d(u[0], u[1], u[2]) >> 9;   // Morton index of the 8^3 super-cell
-                const bool ok = in_binade && tl < t2 && ((__ldg(p.coarse + (sc >> 5)) >> (sc & 31u)) & 1u) == 0u;
+                bool empty = true;
+                for (uint32_t z = sa[2]; z <= sb[2]; ++z)
+                    for (uint32_t y = sa[1]; y <= sb[1]; ++y)
+                        for (uint32_t x = sa[0]; x <= sb[0]; ++x) {
+                            const uint32_t sc = morton3d(x, y, z);   // Morton index of the 8^3 super-cell
+                            empty = empty && ((__ldg(p.coarse + (sc >> 5)) >> (sc & 31u)) & 1u) == 0u;
+                        }
+                const bool ok = in_binade && tl < t2 && empty;
                 const unsigned okm = __ballot_sync(full, ok);
                 const bool reg0 = __shfl_sync(full, reg, 0);
                 f = reg0 ? (okm == full ? 32 : __ffs(~okm) - 1) : 0;    // leading lanes that vouch
@@ -604,46 +618,24 @@ __global__ void __launch_bounds__(128) march_test_kernel(const float* __restrict
     samples_counter[n] = s;
 }
 
-// dilated coarse occupancy of cascade 0: bit s (Morton index of an 8^3-cell super-cell) is set when the super-cell or
-// any of its 26 neighbours holds an occupied cell.  The bitfield is Morton ordered, so a super-cell is 512 consecutive
-// bits = 64 bytes.  One CTA, (G/8)^3 <= 4096 super-cells.
+// coarse occupancy of cascade 0: bit s (Morton index of an 8^3-cell super-cell) is set when the super-cell holds an
+// occupied cell.  The bitfield is Morton ordered, so a super-cell is 512 consecutive bits = 64 bytes.  One CTA,
+// (G/8)^3 <= 4096 super-cells.
 __global__ void __launch_bounds__(1024) coarse_occupancy_kernel(const uint8_t* __restrict__ bits, int G,
                                                                 uint32_t* __restrict__ coarse) {
-    __shared__ uint8_t raw[4096];
     const int S = G >> 3, n_sc = S * S * S;
-    for (int sc = threadIdx.x; sc < n_sc; sc += blockDim.x) {
-        const uint4* p = reinterpret_cast<const uint4*>(bits + (size_t)sc * 64);
-        uint32_t any = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint4 v = __ldg(p + k);
-            any |= v.x | v.y | v.z | v.w;
-        }
-        raw[sc] = any ? 1 : 0;
-    }
-    __syncthreads();
     for (int base = 0; base < n_sc; base += blockDim.x) {
         const int sc = base + threadIdx.x;
         bool occ = false;
         if (sc < n_sc) {
-            // inverse of morton3d for 4 bits per axis
-            int c[3];
+            const uint4* p = reinterpret_cast<const uint4*>(bits + (size_t)sc * 64);
+            uint32_t any = 0;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                uint32_t x = ((uint32_t)sc >> a) & 0x49249249u;
-                x = (x | (x >> 2)) & 0xc30c30c3u;
-                x = (x | (x >> 4)) & 0x0f00f00fu;
-                x = (x | (x >> 8)) & 0xff0000ffu;
-                x = (x | (x >> 16)) & 0x0000ffffu;
-                c[a] = (int)x;
+            for (int k = 0; k < 4; ++k) {
+                const uint4 v = __ldg(p + k);
+                any |= v.x | v.y | v.z | v.w;
             }
-            for (int dz = -1; dz <= 1; ++dz)
-                for (int dy = -1; dy <= 1; ++dy)
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
-                        if (x < 0 || y < 0 || z < 0 || x >= S || y >= S || z >= S) continue;
-                        occ = occ || raw[morton3d((uint32_t)x, (uint32_t)y, (uint32_t)z)] != 0;
-                    }
+            occ = any != 0;
         }
         const unsigned word = __ballot_sync(0xffffffffu, occ);
         if ((threadIdx.x & 31) == 0 && sc < n_sc) coarse[sc >> 5] = word;

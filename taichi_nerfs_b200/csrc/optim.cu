@@ -26,7 +26,11 @@ __device__ __forceinline__ void adam1(float& p, float& g, float& m, float& v, co
     p = p - a.lr_over_bc1 * (m / denom);
 }
 
+// TGrad = float: the gradient is read from (and zeroed in) `grad`.  TGrad = __half: the gradient comes from the fp16
+// transport buffer of the multi-GPU all-reduce (`grad_in`), the fp32 accumulation buffer `grad` is only zeroed.
+template <typename TGrad>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, float* __restrict__ grad,
+                                                   const TGrad* __restrict__ grad_in,
                                                    float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
                                                    __half* __restrict__ shadow, const int32_t* __restrict__ found_inf,
                                                    const float* __restrict__ hyper_dev, AdamArgs a, int64_t n) {
@@ -41,7 +45,15 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, fl
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         if (!skip) {
             float4 p = reinterpret_cast<float4*>(param)[i];
-            float4 g = reinterpret_cast<const float4*>(grad)[i];
+            float4 g;
+            if constexpr (sizeof(TGrad) == 4) {
+                g = reinterpret_cast<const float4*>(grad_in)[i];
+            } else {
+                const uint2 raw = reinterpret_cast<const uint2*>(grad_in)[i];
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                g = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
             float4 m = reinterpret_cast<float4*>(exp_avg)[i];
             float4 v = reinterpret_cast<float4*>(exp_avg_sq)[i];
             adam1(p.x, g.x, m.x, v.x, a);
@@ -59,20 +71,55 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, fl
                 reinterpret_cast<uint2*>(shadow)[i] = pk;
             }
         }
-        if (a.zero_grad) reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.zero_grad && grad != nullptr) reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // tail (n not a multiple of 4)
     for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         if (!skip) {
-            float p = param[i], g = grad[i], m = exp_avg[i], v = exp_avg_sq[i];
+            float p = param[i], g = load_as_float(grad_in, i), m = exp_avg[i], v = exp_avg_sq[i];
             adam1(p, g, m, v, a);
             param[i] = p;
             exp_avg[i] = m;
             exp_avg_sq[i] = v;
             if (shadow) shadow[i] = __float2half_rn(p);
         }
-        if (a.zero_grad) grad[i] = 0.0f;
+        if (a.zero_grad && grad != nullptr) grad[i] = 0.0f;
     }
+}
+
+// fp32 gradient -> fp16 transport buffer (the reference's own gradients are fp16 under autocast); a value that does not
+// fit fp16 becomes inf and is caught by the finite check on the reduced buffer
+__global__ void __launch_bounds__(256) grad_pack_f16_kernel(const float* __restrict__ grad, __half* __restrict__ out,
+                                                            int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 g = reinterpret_cast<const float4*>(grad)[i];
+        const __half2 lo = __floats2half2_rn(g.x, g.y), hi = __floats2half2_rn(g.z, g.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(out)[i] = pk;
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __float2half_rn(grad[i]);
+}
+
+__global__ void __launch_bounds__(256) check_finite_f16_kernel(const __half* __restrict__ grad, int64_t n,
+                                                               int32_t* __restrict__ found_inf) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    const int64_t n8 = n >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const uint4 raw = reinterpret_cast<const uint4*>(grad)[i];
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // exponent all ones = inf or NaN, per half
+            bad |= ((w[k] & 0x7c00u) == 0x7c00u) | ((w[k] & 0x7c000000u) == 0x7c000000u);
+    }
+    for (int64_t i = (n8 << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        bad |= (__half_as_ushort(grad[i]) & 0x7c00u) == 0x7c00u;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1;
 }
 
 // hyper = [lr / bc1, sqrt(bc2), inv_scale, Adam step count t (int bits)].  The LR schedule follows the iteration count
@@ -174,8 +221,8 @@ int ngp_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
     const int64_t work = (n + 3) / 4;
     const int64_t max_blocks = (int64_t)ngp::sm_count() * 8;
     const unsigned grid = (unsigned)min((work + 255) / 256, max_blocks);
-    adam_kernel<<<grid, 256, 0, ngp::as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, (__half*)param_f16_or_null,
-                                                          found_inf_or_null, nullptr, a, n);
+    adam_kernel<float><<<grid, 256, 0, ngp::as_stream(stream)>>>(param, grad, grad, exp_avg, exp_avg_sq,
+                                                                 (__half*)param_f16_or_null, found_inf_or_null, nullptr, a, n);
     NGP_LAUNCHED("adam_kernel");
     return 0;
 }
@@ -201,9 +248,63 @@ int ngp_adam_step_dyn(float* param, float* grad, float* exp_avg, float* exp_avg_
     const int64_t work = (n + 3) / 4;
     const int64_t max_blocks = (int64_t)ngp::sm_count() * 8;
     const unsigned grid = (unsigned)min((work + 255) / 256, max_blocks);
-    adam_kernel<<<grid, 256, 0, ngp::as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, (__half*)param_f16_or_null,
-                                                          found_inf_or_null, hyper_dev, a, n);
+    adam_kernel<float><<<grid, 256, 0, ngp::as_stream(stream)>>>(param, grad, grad, exp_avg, exp_avg_sq,
+                                                                 (__half*)param_f16_or_null, found_inf_or_null, hyper_dev, a, n);
     NGP_LAUNCHED("adam_kernel");
+    return 0;
+}
+
+int ngp_adam_step_dyn_g16(float* param, const void* grad_f16, float* grad_f32_to_zero_or_null, float* exp_avg,
+                          float* exp_avg_sq, void* param_f16_or_null, const int32_t* found_inf_or_null,
+                          const float* hyper_dev, float beta1, float beta2, float eps, int64_t n, void* stream) {
+    NGP_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return 0;
+    NGP_REQUIRE(param && grad_f16 && exp_avg && exp_avg_sq && hyper_dev, "null pointer");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad_f32_to_zero_or_null) |
+                         reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq);
+    NGP_REQUIRE((al & 15) == 0, "param/grad/state must be 16-byte aligned");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(grad_f16) & 7) == 0, "fp16 gradient must be 8-byte aligned");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(param_f16_or_null) & 7) == 0, "fp16 shadow must be 8-byte aligned");
+    AdamArgs a;
+    a.lr_over_bc1 = 0.f;
+    a.bc2_sqrt = 1.f;
+    a.inv_scale = 1.f;
+    a.beta1 = beta1;
+    a.beta2 = beta2;
+    a.eps = eps;
+    a.zero_grad = 1;
+    const int64_t work = (n + 3) / 4;
+    const int64_t max_blocks = (int64_t)ngp::sm_count() * 8;
+    const unsigned grid = (unsigned)min((work + 255) / 256, max_blocks);
+    adam_kernel<__half><<<grid, 256, 0, ngp::as_stream(stream)>>>(param, grad_f32_to_zero_or_null, (const __half*)grad_f16,
+                                                                  exp_avg, exp_avg_sq, (__half*)param_f16_or_null,
+                                                                  found_inf_or_null, hyper_dev, a, n);
+    NGP_LAUNCHED("adam_kernel<f16 grad>");
+    return 0;
+}
+
+int ngp_grad_pack_f16(const float* grad, void* out_f16, int64_t n, void* stream) {
+    NGP_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return 0;
+    NGP_REQUIRE(grad && out_f16, "null pointer");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_f16) & 7) == 0,
+                "grad must be 16-byte, out 8-byte aligned");
+    const int64_t work = (n + 3) / 4;
+    const unsigned grid = (unsigned)min((work + 255) / 256, (int64_t)ngp::sm_count() * 8);
+    grad_pack_f16_kernel<<<grid, 256, 0, ngp::as_stream(stream)>>>(grad, (__half*)out_f16, n);
+    NGP_LAUNCHED("grad_pack_f16_kernel");
+    return 0;
+}
+
+int ngp_check_finite_f16(const void* grad_f16, int64_t n, int32_t* found_inf, void* stream) {
+    NGP_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return 0;
+    NGP_REQUIRE(grad_f16 && found_inf, "null pointer");
+    NGP_REQUIRE((reinterpret_cast<uintptr_t>(grad_f16) & 15) == 0, "grad must be 16-byte aligned");
+    const int64_t work = (n + 7) / 8;
+    const unsigned grid = (unsigned)min((work + 255) / 256, (int64_t)ngp::sm_count() * 8);
+    check_finite_f16_kernel<<<grid, 256, 0, ngp::as_stream(stream)>>>((const __half*)grad_f16, n, found_inf);
+    NGP_LAUNCHED("check_finite_f16_kernel");
     return 0;
 }
 

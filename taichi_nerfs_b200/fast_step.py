@@ -336,6 +336,8 @@ class StaticTrainStep:
         else:
             self._enqueue(sampled, mode)
         self.pending = self.overlap
+        if getattr(self.tr, 'sharded', False):
+            self.tr.master_stale = True     # (the Python side of the update does not run on a graph replay)
 
     def flush(self):
         """Overlap mode: apply the optimizer update of the last step now (before anything reads the parameters:

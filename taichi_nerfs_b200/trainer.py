@@ -93,8 +93,10 @@ class NGPTrainer:
         # sync_master() (called before state_dict / checkpoints).
         import os
         P = self.slices[0][1]
+        # (opt-in, NGP_SHARDED_ADAM=1: on 2 GPUs its four collectives cost more than the bytes they save,
+        # profiles/r2_bench_2gpu_*.json)
         want = (sharded_optimizer if sharded_optimizer is not None
-                else os.environ.get("NGP_SHARDED_ADAM", "1") != "0")
+                else os.environ.get("NGP_SHARDED_ADAM", "0") == "1")
         self.sharded = bool(want and self.world_size > 1 and self._shadow_full is not None
                             and P % (4 * self.world_size) == 0 and self.slices[0][0] == 0)
         if self.sharded:
@@ -104,6 +106,11 @@ class NGPTrainer:
             self.grad_shard = torch.zeros(self.shard, device=dev, dtype=torch.float32)
             self.shadow_shard = torch.zeros(self.shard, device=dev, dtype=torch.float16)
             self.master_stale = False
+        # Several ranks: the gradient travels in fp16 (half the all-reduce bytes).  That is the precision the
+        # reference's own gradients have under autocast (fp16 autograd); the loss scale keeps them in range and an
+        # overflow becomes inf = a skipped step + scale backoff, as with GradScaler.
+        self.grad_f16 = bool(self.world_size > 1 and not self.sharded and os.environ.get("NGP_GRAD_F16", "1") != "0")
+        self.grad16 = torch.zeros(total, device=dev, dtype=torch.float16) if self.grad_f16 else None
 
     # cosine annealing to lr/30 (train.py:159-163, CosineAnnealingLR(T_max=max_steps, eta_min=lr/30))
     def lr_at(self, step: int) -> float:
@@ -147,6 +154,8 @@ class NGPTrainer:
         GradScaler.update(), all on the current stream with device-side scalars (graph-capturable)."""
         if self.sharded and allreduce:
             return self._enqueue_update_sharded(check_finite)
+        if self.grad_f16 and allreduce:
+            return self._enqueue_update_f16()
         L, st = load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
         fg = self.flat_grad
         if allreduce:
@@ -164,6 +173,25 @@ class NGPTrainer:
         if self.dynamic_loss_scale:  # GradScaler.update(): adjusts the scale used by the NEXT step
             check(L.ngp_loss_scale_update(_p(self.scale_state), _p(self.found_inf), 2.0, 0.5, 2000,
                                           float(self.world_size), _p(self.hyper), 0 if check_finite else 1, st))
+
+    def _enqueue_update_f16(self):
+        """Several ranks: pack the gradient to fp16 -> ONE all-reduce of half the bytes -> finite check on the reduced
+        buffer (identical on every rank; catches local inf/NaN and overflow alike) -> Adam reads the fp16 sum and zeroes
+        the fp32 accumulation buffer."""
+        L, st = load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        fg, g16 = self.flat_grad, self.grad16
+        check(L.ngp_grad_pack_f16(_p(fg), _p(g16), fg.numel(), st))
+        parallel.allreduce_gradients(g16, self.pg)
+        check(L.ngp_check_finite_f16(_p(g16), g16.numel(), _p(self.found_inf), st))
+        inv = -1.0 if self.dynamic_loss_scale else parallel.inv_grad_scale(self.loss_scale, self.world_size)
+        check(L.ngp_adam_hyper_update(_p(self.step_dev), self.lr0, self.lr0 / 30, self.max_steps, self.betas[0],
+                                      self.betas[1], inv, _p(self.found_inf), _p(self.hyper), st))
+        check(L.ngp_adam_step_dyn_g16(_p(self.flat_param), _p(g16), _p(fg), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                      _p(self._shadow_full), _p(self.found_inf), _p(self.hyper), self.betas[0],
+                                      self.betas[1], self.eps, fg.numel(), st))
+        if self.dynamic_loss_scale:
+            check(L.ngp_loss_scale_update(_p(self.scale_state), _p(self.found_inf), 2.0, 0.5, 2000,
+                                          float(self.world_size), _p(self.hyper), 0, st))
 
     def _enqueue_update_sharded(self, check_finite: bool):
         """Sharded update (see __init__): inf flag (local check, max over ranks) -> reduce-scatter of the table gradient
