@@ -362,6 +362,7 @@ def run_train(args, cfg_name, cfg):
             step_fn(args.warmup + k, args.warmup + k)
         fast.flush()   # every one of the K updates is applied inside the timed region
     ms_total = timed(timed_steps)
+    trainer.p2p_check()   # (several ranks) no peer barrier gave up waiting
     clock_info = clocks.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0            # eager launches of libngp_b200 kernels
     launches += fast.graph_kernel_launches - graph0       # + kernel nodes executed by CUDA-graph replays
@@ -427,7 +428,11 @@ def run_train(args, cfg_name, cfg):
         "scaling": "weak", "vs_baseline": None, "dtype": "f16" if half else "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"] + "; random-init table+MLP, occupancy B (one warm-up grid update)",
                    "name": cfg_name, "rays_per_gpu": BATCH, "global_batch": world * BATCH, "samples_per_ray": spr,
-                   "occupied_fraction": occupied, "parallelism": f"ray-sharded dp{world}, 1 NCCL all-reduce/step",
+                   "occupied_fraction": occupied, "parallelism": f"ray-sharded dp{world}, " + (
+                       "no collective" if world == 1 else
+                       "peer-memory optimizer step: NVLink P2P reduce-scatter + Adam on the owned 1/N + fp16 all-gather "
+                       "in ONE kernel per rank (csrc/p2p.cu), no NCCL in the step" if trainer.p2p is not None else
+                       "1 NCCL all-reduce/step"),
                    "l2": "no flush: per-step working set (~%d MB of per-sample tensors) exceeds the 126 MB L2; "
                          "new rays every step" % int(spr * BATCH * (2010 if half else 2872) / 1e6),
                    "density_grid_update": f"inside timed loop every {UPDATE_INTERVAL} steps (warm-up mode); "

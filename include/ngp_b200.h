@@ -391,6 +391,37 @@ int ngp_adam_step_dyn_g16(float* param, const void* grad_f16, float* grad_f32_to
                           float* exp_avg_sq, void* param_f16_or_null, const int32_t* found_inf_or_null,
                           const float* hyper_dev, float beta1, float beta2, float eps, int64_t n, void* stream);
 
+/* ---- multi-GPU: gradient exchange fused into the optimizer over NVLink peer memory (csrc/p2p.cu) ----------
+ * What the reference would get from DDP around train.py:197-201 (an NCCL all-reduce of every gradient, then
+ * GradScaler.step / Adam on every rank) as ONE kernel per rank: rank r sums slice r of every rank's gradient buffer
+ * with peer loads (reduce-scatter), runs Adam on that slice only, and stores the updated fp16 table slice into every
+ * rank's shadow table with peer stores (all-gather); the replicated MLP weights are updated by every rank from the
+ * same peer sums.  The buffers peers touch are allocated here and exported through CUDA IPC; the caller exchanges
+ * the opaque handles (e.g. torch.distributed.all_gather_object) and opens its peers' buffers. */
+#define NGP_MAX_PEERS 8
+#define NGP_IPC_HANDLE_BYTES 64
+int ngp_p2p_alloc(int64_t bytes, void** dev_ptr, uint8_t* handle64);   /* zero-filled, 256-byte aligned */
+int ngp_p2p_open(const uint8_t* handle64, void** peer_ptr);            /* a peer's buffer in this process */
+int ngp_p2p_close(void* peer_ptr);
+int ngp_p2p_free(void* dev_ptr);
+int64_t ngp_p2p_flag_bytes(void);                                       /* size of one rank's flag block */
+/* Barrier across the ranks of one box, enqueued on `stream` (graph-capturable): flag_blocks[p] = rank p's flag block
+ * (ngp_p2p_flag_bytes() zero-initialised bytes inside an IPC buffer), *epoch_dev = this rank's barrier count (device
+ * memory, starts at 0, incremented by the kernel).  If found_inf != NULL it is this rank's GradScaler inf flag on entry
+ * and the OR over all ranks on exit.  A rank that waits longer than ~20 s gives up and sets the sticky error word
+ * (flag block word 2 * NGP_MAX_PEERS; later barriers do not wait) instead of hanging the GPU. */
+int ngp_p2p_barrier(void* const* flag_blocks, int rank, int world, uint32_t* epoch_dev, int32_t* found_inf_or_null,
+                    void* stream);
+/* grad_peers[p] / shadow_peers[p]: rank p's flat fp32 gradient buffer / flat fp16 shadow buffer (same layout as
+ * param).  Elements [own_begin, own_end) are this rank's optimizer shard (updated here, shadow broadcast to every
+ * rank); [rep_begin, rep_end) are replicated parameters (updated by every rank, shadow written locally).  Nothing
+ * happens when *found_inf != 0.  hyper_dev as ngp_adam_step_dyn.  The caller brackets the call with two
+ * ngp_p2p_barrier and clears its gradient buffer after the second. */
+int ngp_adam_step_p2p(float* param, void* const* grad_peers, float* exp_avg, float* exp_avg_sq,
+                      void* const* shadow_peers, int rank, int world, const int32_t* found_inf, const float* hyper_dev,
+                      float beta1, float beta2, float eps, int64_t own_begin, int64_t own_end, int64_t rep_begin,
+                      int64_t rep_end, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,13 @@ def _declare(lib):
         "ngp_grad_pack_f16": (ci, [vp, vp, i64, vp]),
         "ngp_check_finite_f16": (ci, [vp, i64, vp, vp]),
         "ngp_adam_step_dyn_g16": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, i64, vp]),
+        "ngp_p2p_alloc": (ci, [i64, C.POINTER(vp), vp]),
+        "ngp_p2p_open": (ci, [vp, C.POINTER(vp)]),
+        "ngp_p2p_close": (ci, [vp]),
+        "ngp_p2p_free": (ci, [vp]),
+        "ngp_p2p_flag_bytes": (i64, []),
+        "ngp_p2p_barrier": (ci, [vp, ci, ci, vp, vp, vp]),
+        "ngp_adam_step_p2p": (ci, [vp, vp, vp, vp, vp, ci, ci, vp, vp, f32, f32, f32, i64, i64, i64, i64, vp]),
         "ngp_frame_begin": (ci, [vp, vp, vp, vp, vp, vp, vp, i64, vp]),
         "ngp_frame_round_begin": (ci, [vp, vp]),
         "ngp_raymarching_round": (ci, [vp, vp, vp, vp, ci, ci, f32, f32, ci, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp]),

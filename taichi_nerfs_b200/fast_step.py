@@ -98,6 +98,8 @@ class StaticTrainStep:
         default_ar = ((trainer.world_size > 1 or os.environ.get("NGP_AR_FORCE") == "1") and enc._clayout.feat_dim == 2
                       and os.environ.get("NGP_AR_OVERLAP", "0") == "1")
         self.overlap_allreduce = bool(overlap_allreduce if overlap_allreduce is not None else default_ar)
+        if self.overlap_allreduce and getattr(trainer, "p2p", None) is not None:
+            self.overlap_allreduce = False   # the peer-memory optimizer step needs no all-reduce at all
         if self.overlap_allreduce and trainer.sharded:
             trainer.sharded = False     # the slice all-reduces replace the reduce-scatter; Adam stays replicated
         # one rank + dynamic loss scale: the backward kernels raise GradScaler's inf flag themselves (a non-finite

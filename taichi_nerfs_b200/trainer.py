@@ -31,7 +31,7 @@ def _p(t):
 class NGPTrainer:
     def __init__(self, model, lr: float = 1e-2, max_steps: int = 20000, loss_scale: float | None = None,
                  betas=(0.9, 0.999), eps: float = 1e-15, process_group=None, dynamic_loss_scale: bool = True,
-                 sharded_optimizer: bool | None = None):
+                 sharded_optimizer: bool | None = None, p2p_optimizer: bool | None = None):
         self.model = model
         self.lr0 = lr
         self.max_steps = max_steps
@@ -51,7 +51,19 @@ class NGPTrainer:
         sizes = [p.numel() for p in self.params]
         pad = [(-s) % 4 for s in sizes]  # keep every slice 16-byte aligned for the float4 Adam kernel
         total = sum(s + q for s, q in zip(sizes, pad))
-        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        # Several ranks on one NVLink box (default; NGP_P2P_ADAM=0 or p2p_optimizer=False keeps NCCL): the gradient
+        # and the fp16 shadow live in a CUDA-IPC buffer that the peers map, and the optimizer step is ONE kernel that
+        # sums the owned 1/N of the gradient with peer loads, runs Adam on it and stores the new fp16 table slice into
+        # every rank's shadow with peer stores (csrc/p2p.cu).  None when unavailable (the NCCL paths below remain).
+        import os
+        self.p2p = None
+        P_, enc_ = sizes[0], model.pos_encoder
+        want_p2p = p2p_optimizer if p2p_optimizer is not None else os.environ.get("NGP_P2P_ADAM", "1") != "0"
+        if (want_p2p and self.world_size > 1 and dev.type == "cuda" and hasattr(enc_, "adopt_shadow")
+                and self.params[0] is enc_.hash_table and P_ % (4 * self.world_size) == 0):
+            from .p2p import PeerRegion
+            self.p2p = PeerRegion.create(total, dev, process_group)
+        self.flat_grad = self.p2p.grad if self.p2p is not None else torch.zeros(total, device=dev, dtype=torch.float32)
         # parameters live in one flat buffer as well (each nn.Parameter becomes a view of it, state_dict is
         # unchanged), so the fused Adam is ONE launch over [hash table | MLP weights]
         self.flat_param = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -82,7 +94,11 @@ class NGPTrainer:
         if hasattr(enc, "adopt_shadow"):
             assert self.params[0] is enc.hash_table, "the hash table must be the first parameter"
             # fp16 copy of the whole flat buffer, rewritten by the Adam pass; the encoder reads its first slice
-            self._shadow_full = self.flat_param.to(torch.float16)
+            if self.p2p is not None:
+                self._shadow_full = self.p2p.shadow
+                self._shadow_full.copy_(self.flat_param)
+            else:
+                self._shadow_full = self.flat_param.to(torch.float16)
             self._shadow = self._shadow_full[:enc.hash_table.numel()]
             enc.adopt_shadow(self._shadow)
 
@@ -97,15 +113,17 @@ class NGPTrainer:
         # profiles/r2_bench_2gpu_*.json)
         want = (sharded_optimizer if sharded_optimizer is not None
                 else os.environ.get("NGP_SHARDED_ADAM", "0") == "1")
-        self.sharded = bool(want and self.world_size > 1 and self._shadow_full is not None
+        self.sharded = bool((want or self.p2p is not None) and self.world_size > 1 and self._shadow_full is not None
                             and P % (4 * self.world_size) == 0 and self.slices[0][0] == 0)
         if self.sharded:
             self.rank = torch.distributed.get_rank(process_group)
             self.shard_lo, hi = parallel.optimizer_shard(P, self.rank, self.world_size)
             self.shard = hi - self.shard_lo
-            self.grad_shard = torch.zeros(self.shard, device=dev, dtype=torch.float32)
-            self.shadow_shard = torch.zeros(self.shard, device=dev, dtype=torch.float16)
+            if self.p2p is None:   # staging buffers of the NCCL reduce-scatter / all-gather
+                self.grad_shard = torch.zeros(self.shard, device=dev, dtype=torch.float32)
+                self.shadow_shard = torch.zeros(self.shard, device=dev, dtype=torch.float16)
             self.master_stale = False
+        assert self.p2p is None or self.sharded
         # Several ranks: the gradient travels in fp16 (half the all-reduce bytes).  That is the precision the
         # reference's own gradients have under autocast (fp16 autograd); the loss scale keeps them in range and an
         # overflow becomes inf = a skipped step + scale backoff, as with GradScaler.
@@ -197,6 +215,8 @@ class NGPTrainer:
         """Sharded update (see __init__): inf flag (local check, max over ranks) -> reduce-scatter of the table gradient
         + all-reduce of the MLP gradients -> Adam on the owned table shard and on the replicated MLP weights ->
         all-gather of the fp16 shadow table -> GradScaler.update()."""
+        if self.p2p is not None:
+            return self._enqueue_update_p2p(check_finite)
         import torch.distributed as dist
         L, st = load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
         fg, P, lo, hi = self.flat_grad, self.slices[0][1], self.shard_lo, self.shard_lo + self.shard
@@ -220,6 +240,35 @@ class NGPTrainer:
             check(L.ngp_loss_scale_update(_p(self.scale_state), _p(self.found_inf), 2.0, 0.5, 2000,
                                           float(self.world_size), _p(self.hyper), 0 if check_finite else 1, st))
         self.master_stale = True
+
+    def _enqueue_update_p2p(self, check_finite: bool):
+        """The sharded update without NCCL (csrc/p2p.cu): [local finite check] -> barrier (all backward passes done;
+        found_inf becomes the OR over the ranks) -> LR / bias-correction scalars -> ONE kernel: peer-load sum of the
+        owned gradient slice + Adam on it + peer-store of the new fp16 table slice into every rank's shadow (the MLP
+        weights: every rank, same sums) -> barrier (everybody has read my gradient and written my shadow) -> clear the
+        local gradient -> GradScaler.update()."""
+        L, st = load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        R, fg, P = self.p2p, self.flat_grad, self.slices[0][1]
+        if check_finite:
+            check(L.ngp_check_finite(_p(fg), fg.numel(), _p(self.found_inf), st))
+        R.barrier(self.found_inf)
+        inv = -1.0 if self.dynamic_loss_scale else parallel.inv_grad_scale(self.loss_scale, self.world_size)
+        check(L.ngp_adam_hyper_update(_p(self.step_dev), self.lr0, self.lr0 / 30, self.max_steps, self.betas[0],
+                                      self.betas[1], inv, _p(self.found_inf), _p(self.hyper), st))
+        check(L.ngp_adam_step_p2p(_p(self.flat_param), R.grad_tab, _p(self.exp_avg), _p(self.exp_avg_sq), R.shadow_tab,
+                                  R.rank, R.world, _p(self.found_inf), _p(self.hyper), self.betas[0], self.betas[1],
+                                  self.eps, self.shard_lo, self.shard_lo + self.shard, P, fg.numel(), st))
+        R.barrier(None)
+        fg.zero_()
+        if self.dynamic_loss_scale:
+            check(L.ngp_loss_scale_update(_p(self.scale_state), _p(self.found_inf), 2.0, 0.5, 2000,
+                                          float(self.world_size), _p(self.hyper), 0 if check_finite else 1, st))
+        self.master_stale = True
+
+    def p2p_check(self):
+        """Host check (synchronises): raises if a peer barrier of this rank timed out (a rank fell out of step)."""
+        if self.p2p is not None and self.p2p.timed_out():
+            raise RuntimeError("NGPTrainer: a peer barrier timed out — the ranks did not run the same steps")
 
     def sync_master(self):
         """Sharded optimizer: make the fp32 master table complete on every rank again (before state_dict(), checkpoints
