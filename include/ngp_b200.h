@@ -224,6 +224,11 @@ int64_t ngp_mlp_save_bytes(int64_t n);
  * silent fall-back when it cannot run).  Same results bit for bit; exists for A/B timing and the parity tests.
  * The environment variable NGP_MLP_FWD overrides the argument. */
 int ngp_mlp_set_impl(int fwd_impl);
+/* The same switch for the backward with fp16 embeddings and saved activations: 0 = auto (v2), 1 = v1 (one tile per CTA,
+ * CTA-wide barrier per round), 2 = v2 (four tile slots per persistent CTA, per-slot mbarriers, separate MMA-issue
+ * warp).  Same MMAs and epilogues, results equal up to the order of the fp32 weight-gradient sums.  The environment
+ * variable NGP_MLP_BWD overrides the argument. */
+int ngp_mlp_set_bwd_impl(int bwd_impl);
 int ngp_mlp_fwd(const void* emb, int emb_dtype, const float* dirs, const ngp_mlp_weights* w,
                 float* sigmas, void* rgbs_f16, void* save, int64_t n, void* stream);
 /* backward: dsigmas [n] fp32, drgbs [n,3] fp16 -> demb [n,32] (emb dtype) and

@@ -57,6 +57,29 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same two instructions for a CONVERGED warp: every lane executes the surrounding (uniform) descriptor arithmetic,
+// one elected lane issues.  With a single active lane (`if (lane == 0)`) the compiler must assume divergent values and
+// moves every descriptor into uniform registers one 32-bit half at a time (R2UR): ~90 cycles per tcgen05.mma measured
+// (profiles/r2_mlp_bwd_v2_trace_single_thread_issue.txt).  Converged, the descriptors are computed on the uniform
+// datapath directly.  elect.sync picks the same lane for the same member mask, so the commit tracks these MMAs.
+__device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -89,7 +112,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
 }
 // ---- descriptors -------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__host__ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
@@ -191,8 +214,20 @@ __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity)
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1u << 24)) __trap();
+        if (!done && ++spins > (1u << 20)) __trap();
     } while (!done);
+}
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
