@@ -225,7 +225,8 @@ int64_t ngp_mlp_save_bytes(int64_t n);
  * The environment variable NGP_MLP_FWD overrides the argument. */
 int ngp_mlp_set_impl(int fwd_impl);
 /* The same switch for the backward with fp16 embeddings and saved activations: 0 = auto (v2), 1 = v1 (one tile per CTA,
- * CTA-wide barrier per round), 2 = v2 (four tile slots per persistent CTA, per-slot mbarriers, separate MMA-issue
+ * CTA-wide barrier per round, MMAs issued by one thread), 2 = v2 (three tile slots per persistent CTA, per-slot
+ * mbarriers, MMAs issued by converged warps with descriptors from constant memory, weight-gradient MMAs on their own
  * warp).  Same MMAs and epilogues, results equal up to the order of the fp32 weight-gradient sums.  The environment
  * variable NGP_MLP_BWD overrides the argument. */
 int ngp_mlp_set_bwd_impl(int bwd_impl);

@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 KEYS = [("hash_fwd_kernel", "hash_fwd"), ("hash_bwd_kernel", "hash_bwd"), ("mlp_fwd", "mlp_fwd"),
-        ("mlp_bwd_kernel", "mlp_bwd"), ("ray_head_fused", "ray_head"), ("adam_kernel", "adam"),
+        ("mlp_bwd", "mlp_bwd"), ("ray_head_fused", "ray_head"), ("adam_kernel", "adam"),
         ("march_train_warp_kernel", "march"), ("composite_round", "composite_round"),
         ("sample_ray_batch", "sampler"), ("check_finite", "check_finite"), ("ray_aabb", "ray_aabb")]
 

@@ -48,7 +48,7 @@ for impl, tag in ((1, "v1 smem"), (2, "v2 tmem")):
             print(f"{name} {tag}: FAILED {e}", flush=True)
 _lib.load().ngp_mlp_set_impl(0)
 outs = {}
-for bwd_impl, tag in ((1, "v1 (1 tile / CTA)"), (2, "v2 (4 slots / CTA)")):
+for bwd_impl, tag in ((1, "v1 (1 tile / CTA)"), (2, "v2 (3 slots / CTA)")):
     _lib.load().ngp_mlp_set_bwd_impl(bwd_impl)
     for name, fn in [
                      ("bwd recompute", lambda: ops.mlp_bwd(emb, dirs, ws, dsig, drgb)),

@@ -656,28 +656,35 @@ __global__ void __launch_bounds__(kThreadsBwd, 2) mlp_bwd_kernel(const TEmb* __r
 // Backward v2 — fp16 embeddings + saved activations, i.e. the training hot path.  The same MMAs and epilogues as
 // mlp_bwd_kernel on a different schedule.  What limits that kernel is not the tensor pipe (22 %), shared memory or
 // issue slots but the ISSUE of its 62 tiny MMAs per tile by one thread: ~90 cycles per tcgen05.mma when a single
-// active lane builds the descriptors (every 32-bit half goes through R2UR), 5.6 k cycles per tile, with the whole CTA
-// waiting at a barrier for that thread in each of the 8 rounds (profiles/r2_mlp_bwd_v2_trace_*.txt).  Here:
-//   * ONE persistent CTA per SM runs FOUR tile slots, each owned by its own warpgroup (one thread per sample row);
-//     four slots fit because a slot needs only 48 KB — the sigma-net recompute (E -> H1) is moved behind the rgb-net
-//     rounds and every buffer is reused as soon as its last reader (an asynchronous MMA included) is done;
-//   * a slot's dX / recompute MMAs (22 per tile) are issued by the slot's own warp 0 — converged, one elected lane,
-//     descriptors as compile-time constants (umma_f16_w) — right behind a 128-thread named barrier: no hand-off to
-//     another warp on the dependent chain  epilogue -> MMA -> commit -> epilogue;
-//   * the weight-gradient MMAs (40 per tile, M = 64, K = the tile's 128 samples) are issued by a separate warp for
-//     all four slots; only this warp touches the weight-gradient accumulators.  Slots hand it their operands through
-//     mbarrier rdw[s] and learn through dwb[s] (tcgen05.commit) that an operand may be overwritten.
+// active lane builds the descriptors in ordinary registers (every 32-bit half goes through R2UR), 5.6 k cycles per
+// tile, with the whole CTA waiting at a barrier for that thread in each of the 8 rounds
+// (profiles/r2_mlp_bwd_v2_trace_single_thread_issue.txt).  Here:
+//   * ONE persistent CTA per SM runs THREE tile slots (64 KB each), each owned by its own warpgroup (one thread per
+//     sample row).  The sigma-net recompute (E -> H1) is moved behind the rgb-net rounds so that six buffers per slot
+//     suffice, and no buffer is overwritten before a full round has passed since its last asynchronous reader was
+//     issued — nothing on the dependent chain ever waits for a weight-gradient MMA;
+//   * a slot's dX / recompute MMAs (22 per tile) are issued by the slot's own warp 0 right behind a 128-thread named
+//     barrier: a CONVERGED warp, one elected lane, descriptors fetched from constant memory straight into uniform
+//     registers (LDCU -> UTCHMMA, ~3 instructions per MMA): no hand-off to another warp on the chain
+//     epilogue -> MMA -> commit -> epilogue;
+//   * the weight-gradient MMAs (40 per tile, M = 64, K = the tile's 128 samples) are issued by a separate warp for all
+//     slots; only this warp touches the weight-gradient accumulators.  Slots hand it their operands through
+//     mbarriers rdw[s][2] and learn through dwb[s][2] (tcgen05.commit) that an operand may be overwritten; two
+//     requests per slot may be outstanding, hence the two alternating barriers (a parity-tracked mbarrier must not be
+//     two phases ahead of its waiter).
 //
-//   round  dX / recompute MMA      weight-gradient MMA     epilogue writes                      waits for (besides D)
-//   L3     D = X3 W3^T                                      H3 = relu(D)            -> H3buf     dW1 of the previous tile
-//   L4     D = H3 W4^T                                      H4 = relu(D)            -> H4buf
-//   R1     D = dO W5               dW5^T += H4^T dO         dH4 = D relu'(H4), in place H4buf    dW5^T
-//   R2     D = dH4 W4              dW4 += dH4^T H3          dH3 = D relu'(H3), in place H3buf;   dW4
-//                                                           E -> H4buf[0:8K]
-//   R3     D = dH3 W3              dW3 += dH3^T X3          dh = D[:,16:32] (+ TruncExp') -> DHbuf
-//   L1     D = E W1^T                                       H1 = relu(D)            -> H3buf     dW3
-//   R4     D = dh W2               dW2^T += H1^T dh         dH1 = D relu'(H1), in place H3buf    dW2^T
-//   R5     D = dH1 W1              dW1 += dH1^T E           dE -> global
+//   round  dX / recompute MMA   weight-gradient MMA (background)   epilogue writes                     waits for (besides D)
+//   L3     D = X3 W3^T                                             H3 = relu(D)          -> H3buf      dW1 of the previous tile
+//   L4     D = H3 W4^T                                             H4 = relu(D)          -> H4buf
+//   R1     D = dO W5            dW5^T += H4^T dO                   dH4 = D relu'(H4)     -> dH4buf
+//   R2     D = dH4 W4           dW4 += dH4^T H3                    dH3 = D relu'(H3)     -> H4buf      dW5^T (H4buf)
+//   R3     D = dH3 W3           dW3 += dH3^T X3                    dh -> DHbuf ; E       -> H3buf      dW4 (H3buf, dH4buf)
+//   L1     D = E W1^T                                              H1 = relu(D)          -> dH4buf
+//   R4     D = dh W2            dW2^T += H1^T dh                   dH1 = D relu'(H1)     -> H4buf      dW3 (H4buf, X3buf)
+//   R5     D = dH1 W1           dW1 += dH1^T E                     dE -> global                        dW2^T (dH4buf, DHbuf)
+//
+// Measured (1.71 M samples, profiles/r2_time_mlp_bwd_v2.txt): 312 us (v1) -> 249 us, bit-identical dL/dE, weight
+// gradients equal up to the order of the fp32 sums; per-round clock trace: profiles/r2_mlp_bwd_v2_trace_3slots.txt.
 constexpr int kSlotsB = 3;
 constexpr int kThreadsB2 = kSlotsB * 128 + 32;   // 416: three slot warpgroups + the weight-gradient issue warp
 constexpr int kIssuerB2 = kSlotsB * 4;           // warp 12
