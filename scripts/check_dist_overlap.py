@@ -65,9 +65,13 @@ for name, (ma, mb) in {"sharded vs replicated": (m1, m2), "sharded + optimizer o
                        "slice all-reduce vs monolithic": (m1, m4), "fp16 transport vs fp32": (m1, m5),
                        "peer-memory optimizer vs replicated": (m1, m6),
                        "peer-memory optimizer + overlap": (m1, m7)}.items():
+    # Adam's first updates are +-lr whatever the gradient's magnitude, so an entry whose gradient sum is ~0 moves in the
+    # opposite direction when the sum is rounded differently (atomic order; fp16 rounding of the transport variant, which
+    # flips more of them): a small fraction of entries may differ by a few lr, the rest agree to 2e-3
+    limit = 1e-2 if name.startswith("fp16 transport") else 2e-3
     for pa, pb in zip(ma.parameters(), mb.parameters()):
         bad = float(((pa - pb).abs() > 2e-3).float().mean())
-        assert bad < 2e-3, (name, bad)
+        assert bad < limit, (name, bad)
 # replicas agree bit for bit: parameters and occupancy grids
 for m in (m1, m2, m3, m4, m5, m6, m7):
     flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
