@@ -1176,7 +1176,14 @@ int launch_bwd_v2(const void* emb, const float* dirs, const ngp_mlp_weights* w, 
                   cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        // one-time set-up (not capturable: the first launch of a process must be an eager one, as in every warm-up):
+        // the set-up below synchronises the stream: if the very first call of the process happens under stream capture,
+        // this launch uses the v1 kernel (-2) and the set-up waits for the first eager call
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            return -2;
+        }
+        // one-time set-up (the first launch of a process is an eager one in every warm-up):
         // ask the kernel where its dynamic shared memory starts, build the descriptor table, upload it
         cudaError_t e = cudaFuncSetAttribute(mlp_bwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemB2);
         uint32_t* d_base = nullptr;
@@ -1348,8 +1355,10 @@ int ngp_mlp_bwd_dyn(const void* emb, int emb_dtype, const float* dirs, const ngp
     if (emb_dtype == NGP_F16) {
         static const int env_impl = [] { const char* e = getenv("NGP_MLP_BWD"); return e ? atoi(e) : -1; }();
         const int impl = env_impl >= 0 ? env_impl : g_bwd_impl;
-        if (save && impl != 1 && n >= kTile)
-            return launch_bwd_v2(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, found_inf_or_null, st);
+        if (save && impl != 1 && n >= kTile) {
+            const int rc = launch_bwd_v2(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, found_inf_or_null, st);
+            if (rc != -2) return rc;   // -2: not set up and the stream is capturing -> v1 below
+        }
         return save ? launch_bwd<__half, true>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, found_inf_or_null, st)
                     : launch_bwd<__half, false>(emb, dirs, w, save, dsigmas, drgbs_f16, demb, grad_w, n, n_dev, found_inf_or_null, st);
     }

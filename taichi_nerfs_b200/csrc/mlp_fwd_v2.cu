@@ -11,7 +11,8 @@
 //     the previous layer's activation in TMEM: the epilogue reads the fp32 accumulators (tcgen05.ld), applies
 //     ReLU / [SH | h] / TruncExp, packs fp16 pairs and writes them back with tcgen05.st — activations never touch
 //     shared memory, only the 20 KB of weights are read from it (per tile ~28 KB instead of ~150 KB);
-//   * roles: warp 8 lane 0 issues TMA loads and all MMAs; warps 0-3 / 4-7 are the epilogue warpgroups of tile slots
+//   * roles: warp 8 issues the TMA loads (lane 0) and all MMAs (converged, one elected lane, descriptors from constant
+//     memory — see the table below the constants); warps 0-3 / 4-7 are the epilogue warpgroups of tile slots
 //     0 / 1 (one thread per sample row).  The issuer alternates between the slots, so slot B's MMA runs under slot A's
 //     epilogue; synchronisation is per slot through mbarriers (acc[s]: tcgen05.commit -> epilogue, rdy[s]: 128
 //     epilogue arrivals -> issuer), there is no CTA-wide barrier inside the tile loop.
@@ -38,6 +39,28 @@ constexpr int kBarV2 = kEmb + kSlots * kStages * kEmbBytes;     // 53,248
 constexpr int kBarFull = kBarV2, kBarAcc = kBarV2 + 32, kBarRdy = kBarV2 + 48, kTmemSlot = kBarV2 + 64;
 constexpr int kSmemV2 = kBarV2 + 80;
 
+// The shared-memory descriptors of every MMA operand (weights: one per 16-wide K step; the layer-1 A operand: two per
+// TMA stage buffer) are constants of the kernel.  They live in constant memory, filled once by the host from the
+// kernel's shared-memory base address: the issuing warp — converged, one elected lane — fetches them straight into
+// uniform registers (LDCU) instead of building them in ordinary registers and moving every 32-bit half with R2UR
+// (~90 cycles per tcgen05.mma for a single active lane; see the backward, mlp.cu).
+__constant__ uint64_t c_f2_w[16];                          // W1: 0-1, W2: 2-5, W3: 6-7, W4: 8-11, W5: 12-15
+__constant__ uint64_t c_f2_a[kSlots * kStages][2];         // layer-1 A: [slot * kStages + stage][k step]
+inline void build_f2_desc(uint32_t smem0, uint64_t* w, uint64_t (*a)[2]) {
+    for (int k = 0; k < 2; ++k) {
+        w[0 + k] = smem_desc(smem0 + kW1 + k * 256, 128, 32 * 16);
+        w[6 + k] = smem_desc(smem0 + kW3 + k * 256, 128, 32 * 16);
+    }
+    for (int k = 0; k < 4; ++k) {
+        w[2 + k] = smem_desc(smem0 + kW2 + k * 256, 128, 64 * 16);
+        w[8 + k] = smem_desc(smem0 + kW4 + k * 256, 128, 64 * 16);
+        w[12 + k] = smem_desc(smem0 + kW5 + k * 256, 128, 64 * 16);
+    }
+    for (int g = 0; g < kSlots * kStages; ++g)
+        for (int k = 0; k < 2; ++k)   // TMA layout: k-chunk stride 2048 (LBO), 8-row group stride 128 (SBO)
+            a[g][k] = smem_desc(smem0 + kEmb + g * kEmbBytes + k * 4096, 2048, 128);
+}
+
 // D[128 x 64] fp32 -> relu -> fp16 pairs -> A[128 x 64] (32 TMEM columns) of the same lane
 __device__ __forceinline__ void epi_hidden_ts(uint32_t d_addr, uint32_t a_addr) {
     uint32_t v[64];
@@ -53,8 +76,12 @@ __device__ __forceinline__ void epi_hidden_ts(uint32_t d_addr, uint32_t a_addr) 
 __global__ void __launch_bounds__(kThreadsV2, 2)
 mlp_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_emb, const float* __restrict__ dirs, ngp_mlp_weights w,
                   float* __restrict__ sigmas, __half* __restrict__ rgbs, __half* __restrict__ save, int64_t n_max,
-                  const int32_t* __restrict__ n_dev) {
+                  const int32_t* __restrict__ n_dev, uint32_t* __restrict__ probe_smem_base) {
     extern __shared__ __align__(128) uint8_t smem[];
+    if (probe_smem_base != nullptr) {   // set-up launch: where this kernel's dynamic shared memory starts
+        if (threadIdx.x == 0) *probe_smem_base = smem_u32(smem);
+        return;
+    }
     const int64_t n = n_dev ? min(n_max, max((int64_t)*n_dev, (int64_t)0)) : n_max;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -84,87 +111,78 @@ mlp_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_emb, const float* __r
     // tile j of slot s (this CTA): blockIdx.x + (kSlots * j + s) * G
 
     if (warp == kIssuerWarp) {
+        // ============ TMA producer + MMA issuer: the whole warp, converged; lane 0 issues the TMA loads, one
+        // elected lane the MMAs (descriptors from constant memory) ============
+        if (lane == 0) tma_prefetch_desc(&tmap_emb);
+        int64_t cnt[kSlots];
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+            const int64_t first = (int64_t)blockIdx.x + s * G;
+            cnt[s] = first < n_tiles ? (n_tiles - 1 - first) / (kSlots * G) + 1 : 0;
+        }
+        auto issue_tma = [&](int s, int64_t j) {   // lane 0 only
+            const int64_t tile = (int64_t)blockIdx.x + (kSlots * j + s) * G;
+            const uint32_t bar = smem_u32(smem + kBarFull + 8 * (s * kStages + (int)(j & 1)));
+            const uint32_t dst = smem_u32(smem + kEmb + (s * kStages + (int)(j & 1)) * kEmbBytes);
+            mbar_arrive_expect_tx(bar, kEmbBytes);
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc)   // 8 fp16 columns x 128 rows -> one 2 KB column of core matrices
+                tma_load_2d(dst + kc * 2048, &tmap_emb, kc * 8, (int32_t)(tile * kTile), bar);
+        };
         if (lane == 0) {
-            // ======================= TMA producer + MMA issuer (one thread) =======================
-            tma_prefetch_desc(&tmap_emb);
-            int64_t cnt[kSlots];
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                const int64_t first = (int64_t)blockIdx.x + s * G;
-                cnt[s] = first < n_tiles ? (n_tiles - 1 - first) / (kSlots * G) + 1 : 0;
-            }
-            auto issue_tma = [&](int s, int64_t j) {
-                const int64_t tile = (int64_t)blockIdx.x + (kSlots * j + s) * G;
-                const uint32_t bar = smem_u32(smem + kBarFull + 8 * (s * kStages + (int)(j & 1)));
-                const uint32_t dst = smem_u32(smem + kEmb + (s * kStages + (int)(j & 1)) * kEmbBytes);
-                mbar_arrive_expect_tx(bar, kEmbBytes);
-#pragma unroll
-                for (int kc = 0; kc < 4; ++kc)   // 8 fp16 columns x 128 rows -> one 2 KB column of core matrices
-                    tma_load_2d(dst + kc * 2048, &tmap_emb, kc * 8, (int32_t)(tile * kTile), bar);
-            };
 #pragma unroll
             for (int s = 0; s < kSlots; ++s)
                 for (int64_t j = 0; j < kStages && j < cnt[s]; ++j) issue_tma(s, j);
+        }
+        __syncwarp();
+        constexpr uint32_t id64 = idesc_f16(kTile, 64), id16 = idesc_f16(kTile, 16);
 
-            // weight descriptors (B operands, K-major no-swizzle: LBO = 128, SBO = K * 16), one per 16-wide K step
-            const uint32_t aW1 = smem_u32(smem + kW1), aW2 = smem_u32(smem + kW2), aW3 = smem_u32(smem + kW3),
-                           aW4 = smem_u32(smem + kW4), aW5 = smem_u32(smem + kW5);
-            uint64_t dW1[2], dW2[4], dW3[2], dW4[4], dW5[4];
+        uint32_t rdy_phase[kSlots] = {0, 0};
+        const int64_t jmax = cnt[0] > cnt[1] ? cnt[0] : cnt[1];
+        for (int64_t j = 0; j < jmax; ++j) {
+            const bool odd = (j & 1) != 0;   // which TMA stage this tile's embedding is in (warp-uniform)
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                dW1[k] = smem_desc(aW1 + k * 256, 128, 32 * 16);
-                dW3[k] = smem_desc(aW3 + k * 256, 128, 32 * 16);
-            }
+            for (int l = 0; l < 5; ++l) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                dW2[k] = smem_desc(aW2 + k * 256, 128, 64 * 16);
-                dW4[k] = smem_desc(aW4 + k * 256, 128, 64 * 16);
-                dW5[k] = smem_desc(aW5 + k * 256, 128, 64 * 16);
-            }
-            constexpr uint32_t id64 = idesc_f16(kTile, 64), id16 = idesc_f16(kTile, 16);
-
-            uint32_t rdy_phase[kSlots] = {0, 0};
-            const int64_t jmax = cnt[0] > cnt[1] ? cnt[0] : cnt[1];
-            for (int64_t j = 0; j < jmax; ++j) {
+                for (int s = 0; s < kSlots; ++s) {
+                    if (j >= cnt[s]) continue;
+                    const uint32_t D = tmem_base + s * kSlotCols, A = D + kColA;
+                    const uint32_t acc = smem_u32(smem + kBarAcc + 8 * s);
+                    // l == 0: the slot is free (epilogue of its previous tile has read its outputs);
+                    // l >= 1: the epilogue has written layer l's A operand into TMEM
+                    mbar_wait_bounded(smem_u32(smem + kBarRdy + 8 * s), rdy_phase[s]);
+                    rdy_phase[s] ^= 1;
+                    if (l == 0) {
+                        const int stg = s * kStages + (odd ? 1 : 0);
+                        mbar_wait_bounded(smem_u32(smem + kBarFull + 8 * stg), (uint32_t)((j >> 1) & 1));
+                        tc_fence_after();
+                        if (odd) {
 #pragma unroll
-                for (int l = 0; l < 5; ++l) {
-#pragma unroll
-                    for (int s = 0; s < kSlots; ++s) {
-                        if (j >= cnt[s]) continue;
-                        const uint32_t D = tmem_base + s * kSlotCols, A = D + kColA;
-                        const uint32_t acc = smem_u32(smem + kBarAcc + 8 * s);
-                        // l == 0: the slot is free (epilogue of its previous tile has read its outputs);
-                        // l >= 1: the epilogue has written layer l's A operand into TMEM
-                        mbar_wait_bounded(smem_u32(smem + kBarRdy + 8 * s), rdy_phase[s]);
-                        rdy_phase[s] ^= 1;
-                        if (l == 0) {
-                            const int stg = s * kStages + (int)(j & 1);
-                            mbar_wait_bounded(smem_u32(smem + kBarFull + 8 * stg), (uint32_t)((j >> 1) & 1));
-                            tc_fence_after();
-                            const uint32_t a = smem_u32(smem + kEmb + stg * kEmbBytes);
-#pragma unroll
-                            for (int k = 0; k < 2; ++k)   // TMA layout: k-chunk stride 2048 (LBO), 8-row group stride 128 (SBO)
-                                umma_f16(D, smem_desc(a + k * 4096, 2048, 128), dW1[k], id64, k > 0);
+                            for (int k = 0; k < 2; ++k) umma_f16_w(D, c_f2_a[s * kStages + 1][k], c_f2_w[0 + k], id64, k > 0);
                         } else {
-                            tc_fence_after();
-                            if (l == 1) {
-                                // layer 1 of tile j has completed (its epilogue ran): the stage is free for tile j + 2
-                                if (j + kStages < cnt[s]) issue_tma(s, j + kStages);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) umma_f16_ts(D, A + k * 8, dW2[k], id16, k > 0);
-                            } else if (l == 2) {
-#pragma unroll
-                                for (int k = 0; k < 2; ++k) umma_f16_ts(D, A + k * 8, dW3[k], id64, k > 0);
-                            } else if (l == 3) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) umma_f16_ts(D, A + k * 8, dW4[k], id64, k > 0);
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) umma_f16_ts(D, A + k * 8, dW5[k], id16, k > 0);
-                            }
+                            for (int k = 0; k < 2; ++k) umma_f16_w(D, c_f2_a[s * kStages + 0][k], c_f2_w[0 + k], id64, k > 0);
                         }
-                        umma_commit(acc);
+                    } else {
+                        tc_fence_after();
+                        if (l == 1) {
+                            // layer 1 of tile j has completed (its epilogue ran): the stage is free for tile j + 2
+                            if (lane == 0 && j + kStages < cnt[s]) issue_tma(s, j + kStages);
+                            __syncwarp();
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_f16_ts_w(D, A + k * 8, c_f2_w[2 + k], id16, k > 0);
+                        } else if (l == 2) {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) umma_f16_ts_w(D, A + k * 8, c_f2_w[6 + k], id64, k > 0);
+                        } else if (l == 3) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_f16_ts_w(D, A + k * 8, c_f2_w[8 + k], id64, k > 0);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_f16_ts_w(D, A + k * 8, c_f2_w[12 + k], id16, k > 0);
+                        }
                     }
+                    umma_commit_w(acc);
                 }
             }
         }
@@ -313,9 +331,34 @@ int mlp_fwd_v2_launch(const void* emb_f16, const float* dirs, const ngp_mlp_weig
     }
     static bool configured = false;
     if (!configured) {
+        // the set-up synchronises the stream: under stream capture this launch goes to the v1 kernel (-2) and the set-up
+        // waits for the first eager call (every warm-up makes one)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            return -2;
+        }
         cudaError_t e = cudaFuncSetAttribute(mlp_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemV2);
+        uint32_t* d_base = nullptr;
+        uint32_t h_base = 0;
+        if (e == cudaSuccess) e = cudaMalloc(&d_base, sizeof(uint32_t));
+        if (e == cudaSuccess) {
+            mlp_fwd_v2_kernel<<<1, kThreadsV2, kSmemV2, st>>>(tmap, nullptr, *w, nullptr, nullptr, nullptr, 0, nullptr, d_base);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_base, d_base, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) {
+            static uint64_t hw[16], ha[kSlots * kStages][2];
+            build_f2_desc(h_base, hw, ha);
+            e = cudaMemcpyToSymbolAsync(c_f2_w, hw, sizeof(hw), 0, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_f2_a, ha, sizeof(ha), 0, cudaMemcpyHostToDevice, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (d_base) cudaFree(d_base);
         if (e != cudaSuccess) {
-            set_error("mlp_fwd_v2_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            set_error("mlp_fwd_v2_kernel: set-up: %s", cudaGetErrorString(e));
             return (int)e;
         }
         configured = true;
@@ -324,7 +367,8 @@ int mlp_fwd_v2_launch(const void* emb_f16, const float* dirs, const ngp_mlp_weig
     const int64_t want = (n_tiles + kSlots - 1) / kSlots;
     const int64_t max_ctas = (int64_t)sm_count() * 2;   // 256 TMEM columns + 53 KB shared memory per CTA
     const unsigned grid = (unsigned)(want < max_ctas ? want : max_ctas);
-    mlp_fwd_v2_kernel<<<grid, kThreadsV2, kSmemV2, st>>>(tmap, dirs, *w, sigmas, (__half*)rgbs, (__half*)save, n, n_dev);
+    mlp_fwd_v2_kernel<<<grid, kThreadsV2, kSmemV2, st>>>(tmap, dirs, *w, sigmas, (__half*)rgbs, (__half*)save, n, n_dev,
+                                                         nullptr);
     count_launch();
     return check_launch("mlp_fwd_v2_kernel");
 }

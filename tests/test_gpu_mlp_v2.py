@@ -85,3 +85,36 @@ def test_mlp_fwd_v2_device_side_count(impl):
     torch.cuda.synchronize()
     assert torch.equal(sig[:n], s_ref) and torch.equal(rgb[:n], r_ref)
     assert bool((sig[n:] == -7.0).all()) and bool((rgb[n:] == -7.0).all())
+
+
+@pytest.fixture()
+def bwd_impl():
+    from taichi_nerfs_b200 import _lib
+    lib = _lib.load()
+    yield lambda k: _lib.check(lib.ngp_mlp_set_bwd_impl(k), "ngp_mlp_set_bwd_impl")
+    lib.ngp_mlp_set_bwd_impl(0)
+
+
+@pytest.mark.parametrize("n", [128, 129, 5000, 148 * 3 * 128 + 1, 300 * 128 * 2 + 77])
+def test_mlp_bwd_v2_equals_v1(bwd_impl, n):
+    """Backward v2 (three slots per persistent CTA, MMAs issued by converged warps) against v1 (one tile per CTA): the
+    same MMAs on the same operands and the same epilogue arithmetic, so dL/dE is bit-identical; the weight gradients
+    are sums over all tiles accumulated in a different order (fp32 in TMEM, then fp32 atomics per CTA)."""
+    from taichi_nerfs_b200 import ops
+    rng = np.random.default_rng(n)
+    emb = T(rng.standard_normal((n, 32)).astype(np.float16))
+    dirs = T(rng.standard_normal((n, 3)).astype(np.float32))
+    ws = [T(w) for w in _weights(rng)]
+    dsig = T((rng.standard_normal(n) * 1e-2).astype(np.float32))
+    drgb = T((rng.standard_normal((n, 3)) * 1e-2).astype(np.float16))
+    _, _, save = ops.mlp_fwd(emb, dirs, ws, with_save=True)
+    bwd_impl(1)
+    de1, gw1 = ops.mlp_bwd(emb, dirs, ws, dsig, drgb, save=save)
+    bwd_impl(2)
+    de2, gw2 = ops.mlp_bwd(emb, dirs, ws, dsig, drgb, save=save)
+    de3, gw3 = ops.mlp_bwd(emb, dirs, ws, dsig, drgb, save=save)     # a second launch: no state left behind
+    torch.cuda.synchronize()
+    assert torch.equal(de1, de2) and torch.equal(de2, de3)
+    scale = float(gw1.abs().max())
+    assert float((gw1 - gw2).abs().max()) <= 2e-5 * scale
+    assert float((gw2 - gw3).abs().max()) <= 2e-5 * scale
