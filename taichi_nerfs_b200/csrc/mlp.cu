@@ -1174,8 +1174,11 @@ int g_bwd_impl = 0;
 int launch_bwd_v2(const void* emb, const float* dirs, const ngp_mlp_weights* w, const void* save, const float* dsigmas,
                   const void* drgbs, void* demb, float* grad_w, int64_t n, const int32_t* n_dev, int32_t* found_inf,
                   cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    // (the descriptor table lives in constant memory, i.e. per device: one flag per device of this process)
+    static bool configured_dev[64] = {};
+    int dev_id = 0;
+    if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) dev_id = 0;
+    if (!configured_dev[dev_id]) {
         // the set-up below synchronises the stream: if the very first call of the process happens under stream capture,
         // this launch uses the v1 kernel (-2) and the set-up waits for the first eager call
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -1208,7 +1211,7 @@ int launch_bwd_v2(const void* emb, const float* dirs, const ngp_mlp_weights* w, 
             ngp::set_error("mlp_bwd_v2_kernel: set-up: %s", cudaGetErrorString(e));
             return (int)e;
         }
-        configured = true;
+        configured_dev[dev_id] = true;
     }
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int64_t max_ctas = (int64_t)ngp::sm_count();   // 212 KB of shared memory + all 512 TMEM columns per CTA

@@ -329,8 +329,11 @@ int mlp_fwd_v2_launch(const void* emb_f16, const float* dirs, const ngp_mlp_weig
         set_error("mlp_fwd_v2: cuTensorMapEncodeTiled failed (%d)", (int)r);
         return -2;
     }
-    static bool configured = false;
-    if (!configured) {
+    // (the descriptor table lives in constant memory, i.e. per device: one flag per device of this process)
+    static bool configured_dev[64] = {};
+    int dev_id = 0;
+    if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) dev_id = 0;
+    if (!configured_dev[dev_id]) {
         // the set-up synchronises the stream: under stream capture this launch goes to the v1 kernel (-2) and the set-up
         // waits for the first eager call (every warm-up makes one)
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -361,7 +364,7 @@ int mlp_fwd_v2_launch(const void* emb_f16, const float* dirs, const ngp_mlp_weig
             set_error("mlp_fwd_v2_kernel: set-up: %s", cudaGetErrorString(e));
             return (int)e;
         }
-        configured = true;
+        configured_dev[dev_id] = true;
     }
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int64_t want = (n_tiles + kSlots - 1) / kSlots;
